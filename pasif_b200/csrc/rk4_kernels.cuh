@@ -1,0 +1,303 @@
+// rk4_kernels.cuh -- register-resident RK4 forward / adjoint kernels for small polynomial ODE systems (sm_100a).
+//
+// One thread integrates ONE trajectory = (system instance, excitation) for the whole time range handed to the
+// launch: state, RK4 stage vector and running stage sum live in registers, coefficients of the instance are
+// loaded once into registers, and the only per-step memory traffic is one excitation sample (forward) or the
+// forward state of the step (adjoint).  There are no atomics, no per-step launches and no inter-thread
+// communication: the (instance x excitation) batch is embarrassingly parallel.
+//
+// The sparsity pattern of the system is a COMPILE-TIME traits class `P` (constexpr index tables), so every
+// state/stage array index is a literal after unrolling and ptxas keeps the arrays in registers.  The same header
+// is compiled ahead of time for the reference's example systems (patterns_aot.inc) and at run time through NVRTC
+// for any other pattern (engine.cu); it must therefore stay free of #includes.
+//
+// What it replaces in the reference (per RK4 step: ~17 kernel launches + cuSPARSE SpMM + atomics):
+//   fwdStep / derivatives / modterpolator      src/__GpuDriver.cu:693-713, 785-838, 840-890
+//   SpTdV, applyForces, updateSlope, integrate src/kernels.cu:21-63, 71-88, 201-229
+//   bwdStep + request/half/previous_setpoint   src/__GpuDriver.cu:746-783, src/kernels.cu:162-195
+//
+// Arithmetic contract (parity with the reference):
+//   y_r  = sum_k K[r,k] x_k (CSR order) ; then Gamma, Lambda, Psi terms in hand-off order ; then F_r * e
+//   each term  ((val * x_a) * p_b) [* p_c [* p_d]]  -- same association as SpTdV, last multiply fused into the add
+//   mi   = q + dt * m                               (updateSlope)
+//   q   += h6 * (m1 + 2 m2 + 2 m3 + m4)             (integrate; accumulated left to right in `s`, which is
+//                                                    bit-identical because 2*m is exact)
+#pragma once
+
+#ifndef PASIF_BLOCK
+#define PASIF_BLOCK 128
+#endif
+
+#define PASIF_DEV __device__ __forceinline__
+
+namespace pasif {
+
+// ------------------------------------------------------------------------------------------------ launch arguments
+template <typename T>
+struct FwdArgs {
+  const T* coef;        // [NC][n_inst]   instance-minor coefficient table (K, Gamma, Lambda, Psi, F values)
+  const T* q_in;        // [N][n_traj]    start state (trajectory-minor SoA); nullptr -> broadcast `ic`
+  const T* ic;          // [N][n_inst]
+  T* q_out;             // [N][n_traj]    end state, may alias q_in; nullptr -> not written
+  const T* exc;         // gated force samples: FULL-step mode [t][E] ; HALF-step mode [u][E], u = 2t + half
+  int n_inst, E, n_traj;
+  int t0, t1;           // steps t0 <= t < t1
+  int half_mode;        // 0: stages use e[t], e[t], e[t], e[t+1] ; 1: f[2t], f[2t+1], f[2t+1], f[2t+2]
+  T h, h2, h6;
+  // periodic save after step t when (t + save_phase) % save_every == 0, into slot (t + save_phase) / save_every
+  T* save_ptr;          // layout 0: [slot][N][n_traj]   layout 1 (user): [slot][E][n_glob] through varmap
+  int save_every, save_phase, save_layout, save_slots;
+  int n_glob;
+  const int* varmap;    // [N][n_inst] global state index of local variable i of instance j
+  // dense save (adjoint recompute): needed forward variables after EVERY step, [t - t0][NV][n_traj]
+  T* dense_ptr;
+  // final state scattered to the user layout [e][n_glob] (getAmplitudes)
+  T* final_user;
+};
+
+template <typename T>
+struct BwdArgs {
+  const T* coef;        // [NCA][n_inst]  adjoint coefficient table
+  T* lam;               // [NA][n_traj]   adjoint state, in/out
+  const T* dense;       // [i][NV][n_traj] forward state after step (t0 + i), i in [0, len)
+  const T* prev;        // [NF][n_traj]   forward state standing in for index i = -1 (a checkpoint slot)
+  int len;              // number of backward steps
+  int alias_local;      // literal-reference mode: local index of the aliased scratch slot (quirk A3) or -1000000
+  int n_inst, E, n_traj;
+  T h, h2, h6;
+};
+
+// ------------------------------------------------------------------------------------------------ derivative
+// y = K x + Gamma:(x,p) + Lambda:(x,p,p) + Psi:(x,p,p,p) + F fe        (forward: p == x)
+template <typename T, class P, int NX, int NP_>
+PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::NC > 0 ? P::NC : 1], T fe,
+                          T (&y)[NX]) {
+#pragma unroll
+  for (int r = 0; r < P::N; ++r) y[r] = T(0);
+#pragma unroll
+  for (int k = 0; k < P::NNZK; ++k) y[P::k_row(k)] = fma(c[P::OFF_K + k], x[P::k_col(k)], y[P::k_row(k)]);
+#pragma unroll
+  for (int k = 0; k < P::NNZG; ++k)
+    y[P::g_o(k)] = fma(c[P::OFF_G + k] * x[P::g_a(k)], p[P::g_b(k)], y[P::g_o(k)]);
+#pragma unroll
+  for (int k = 0; k < P::NNZL; ++k)
+    y[P::l_o(k)] = fma(c[P::OFF_L + k] * x[P::l_a(k)] * p[P::l_b(k)], p[P::l_c(k)], y[P::l_o(k)]);
+#pragma unroll
+  for (int k = 0; k < P::NNZP; ++k)
+    y[P::p_o(k)] = fma(c[P::OFF_P + k] * x[P::p_a(k)] * p[P::p_b(k)] * p[P::p_c(k)], p[P::p_d(k)], y[P::p_o(k)]);
+#pragma unroll
+  for (int k = 0; k < P::NF; ++k) y[P::f_row(k)] = fma(c[P::OFF_F + k], fe, y[P::f_row(k)]);
+}
+
+// one classical RK4 step of the forward system; fa/fb/fc = force sample of stage 1 / stages 2,3 / stage 4
+template <typename T, class P>
+PASIF_DEV void rk4_forward_step(T (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1], T fa, T fb, T fc, T h, T h2, T h6) {
+  T m[P::N], s[P::N], mi[P::N];
+  derivative<T, P, P::N, P::N>(q, q, c, fa, m);
+#pragma unroll
+  for (int i = 0; i < P::N; ++i) { s[i] = m[i]; mi[i] = fma(h2, m[i], q[i]); }
+  derivative<T, P, P::N, P::N>(mi, mi, c, fb, m);
+#pragma unroll
+  for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h2, m[i], q[i]); }
+  derivative<T, P, P::N, P::N>(mi, mi, c, fb, m);
+#pragma unroll
+  for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h, m[i], q[i]); }
+  derivative<T, P, P::N, P::N>(mi, mi, c, fc, m);
+#pragma unroll
+  for (int i = 0; i < P::N; ++i) q[i] = fma(h6, s[i] + m[i], q[i]);
+}
+
+// ------------------------------------------------------------------------------------------------ forward kernel
+// PF: forward pattern.  DV: list of forward variables written by the dense save (DV::NV may be 0).
+template <typename T, class PF, class DV>
+PASIF_DEV void forward_body(const FwdArgs<T>& a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_traj) return;
+  const int inst = p / a.E;
+  const int e = p - inst * a.E;
+  constexpr int N = PF::N;
+  constexpr int NC = PF::NC > 0 ? PF::NC : 1;
+
+  T c[NC];
+#pragma unroll
+  for (int k = 0; k < PF::NC; ++k) c[k] = a.coef[(long long)k * a.n_inst + inst];
+  T q[N];
+  if (a.q_in) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = a.q_in[(long long)i * a.n_traj + p];
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) q[i] = a.ic[(long long)i * a.n_inst + inst];
+  }
+
+  const T h = a.h, h2 = a.h2, h6 = a.h6;
+  const long long E = a.E;
+  // periodic-save bookkeeping without a per-step modulo
+  int save_cnt = -1, save_slot = 0;
+  if (a.save_ptr) {
+    const int u = a.t0 + a.save_phase;
+    save_slot = (u + a.save_every - 1) / a.save_every;          // first slot index with slot*every >= u
+    save_cnt = save_slot * a.save_every - u;                    // steps (beyond t0) until that save fires
+  }
+  T* dense = a.dense_ptr ? a.dense_ptr + p : nullptr;
+
+  if (!a.half_mode) {
+    // register ring of gated excitation samples: e0 = e[t], e1 = e[t+1], ... prefetch distance 4 steps
+    const T* ex = a.exc + (long long)a.t0 * E + e;
+    T e0 = ex[0], e1 = ex[E], e2 = ex[2 * E], e3 = ex[3 * E];
+    ex += 4 * E;
+    for (int t = a.t0; t < a.t1; ++t) {
+      const T e4 = *ex;                                          // e[t+4] (buffer is zero-padded past t1)
+      ex += E;
+      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6);
+      e0 = e1; e1 = e2; e2 = e3; e3 = e4;
+      if (DV::NV > 0 && dense) {
+#pragma unroll
+        for (int v = 0; v < DV::NV; ++v) dense[(long long)v * a.n_traj] = q[DV::nv(v)];
+        dense += (long long)DV::NV * a.n_traj;
+      }
+      if (save_cnt == 0) {
+        if (save_slot < a.save_slots) {
+          if (a.save_layout == 0) {
+            T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
+          } else {
+            T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+          }
+        }
+        ++save_slot;
+        save_cnt = a.save_every;
+      }
+      --save_cnt;
+    }
+  } else {
+    // half-step mode (interpolation table): f[2t], f[2t+1], f[2t+2] -- preprocessed on the device by
+    // interp_force_kernel; two new samples per step
+    const T* ex = a.exc + (long long)(2 * a.t0) * E + e;
+    T f0 = ex[0];
+    ex += E;
+    for (int t = a.t0; t < a.t1; ++t) {
+      const T f1 = ex[0], f2 = ex[E];
+      ex += 2 * E;
+      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6);
+      f0 = f2;
+      if (DV::NV > 0 && dense) {
+#pragma unroll
+        for (int v = 0; v < DV::NV; ++v) dense[(long long)v * a.n_traj] = q[DV::nv(v)];
+        dense += (long long)DV::NV * a.n_traj;
+      }
+      if (save_cnt == 0) {
+        if (save_slot < a.save_slots) {
+          if (a.save_layout == 0) {
+            T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
+          } else {
+            T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
+#pragma unroll
+            for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+          }
+        }
+        ++save_slot;
+        save_cnt = a.save_every;
+      }
+      --save_cnt;
+    }
+  }
+
+  if (a.q_out) {
+#pragma unroll
+    for (int i = 0; i < N; ++i) a.q_out[(long long)i * a.n_traj + p] = q[i];
+  }
+  if (a.final_user) {
+    T* dst = a.final_user + (long long)e * a.n_glob;
+#pragma unroll
+    for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ adjoint kernel
+// PA: adjoint pattern: N = adjoint state size, tensor "p" indices refer to the needed-forward-variable list
+// (PA::NV entries, PA::nv(v) = local forward index).  RK4 on the unforced adjoint ODE, walking the recomputed
+// chunk backwards; forward state per stage = q_i, (q_i + q_{i-1})/2, q_{i-1}  (src/__GpuDriver.cu:746-783).
+template <typename T, class PA>
+PASIF_DEV void backward_body(const BwdArgs<T>& a) {
+  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  if (p >= a.n_traj) return;
+  const int inst = p / a.E;
+  constexpr int N = PA::N;
+  constexpr int NC = PA::NC > 0 ? PA::NC : 1;
+  constexpr int NV = PA::NV > 0 ? PA::NV : 1;
+
+  T c[NC];
+#pragma unroll
+  for (int k = 0; k < PA::NC; ++k) c[k] = a.coef[(long long)k * a.n_inst + inst];
+  T lam[N];
+#pragma unroll
+  for (int i = 0; i < N; ++i) lam[i] = a.lam[(long long)i * a.n_traj + p];
+
+  const T h = a.h, h2 = a.h2, h6 = a.h6;
+  const long long stride = (long long)PA::NV * a.n_traj;
+  const T* d = a.dense + p + (long long)(a.len - 1) * stride;    // state index i = len-1
+  T qa[NV], qn[NV], qh[NV];
+#pragma unroll
+  for (int v = 0; v < PA::NV; ++v) qa[v] = d[(long long)v * a.n_traj];
+  // software prefetch: qn = state i-1 of the CURRENT iteration, loaded one iteration ahead
+  if (a.len >= 2) {
+#pragma unroll
+    for (int v = 0; v < PA::NV; ++v) qn[v] = d[(long long)v * a.n_traj - stride];
+  } else {
+#pragma unroll
+    for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
+  }
+
+  for (int i = a.len - 1; i >= 0; --i) {
+    // qb = forward state of index i-1.  Literal-reference mode: when i-1 is the aliased scratch slot the reference
+    // reads back what it has just written there, i.e. the current qa.
+    T qb[NV];
+    const bool aliased = (i - 1 == a.alias_local);
+#pragma unroll
+    for (int v = 0; v < PA::NV; ++v) qb[v] = aliased ? qa[v] : qn[v];
+    // prefetch state i-2 for the next iteration
+    if (i >= 2) {
+      const T* dn = d - 2 * stride;
+#pragma unroll
+      for (int v = 0; v < PA::NV; ++v) qn[v] = dn[(long long)v * a.n_traj];
+    } else if (i == 1) {
+#pragma unroll
+      for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
+    }
+    d -= stride;
+#pragma unroll
+    for (int v = 0; v < PA::NV; ++v) qh[v] = T(.5) * (qa[v] + qb[v]);
+
+    T m[N], s[N], mi[N];
+    derivative<T, PA, N, NV>(lam, qa, c, T(0), m);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { s[k] = m[k]; mi[k] = fma(h2, m[k], lam[k]); }
+    derivative<T, PA, N, NV>(mi, qh, c, T(0), m);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h2, m[k], lam[k]); }
+    derivative<T, PA, N, NV>(mi, qh, c, T(0), m);
+#pragma unroll
+    for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h, m[k], lam[k]); }
+    derivative<T, PA, N, NV>(mi, qb, c, T(0), m);
+#pragma unroll
+    for (int k = 0; k < N; ++k) lam[k] = fma(h6, s[k] + m[k], lam[k]);
+#pragma unroll
+    for (int v = 0; v < PA::NV; ++v) qa[v] = qb[v];
+  }
+
+#pragma unroll
+  for (int i = 0; i < N; ++i) a.lam[(long long)i * a.n_traj + p] = lam[i];
+}
+
+struct NoDense {
+  static constexpr int NV = 0;
+  PASIF_DEV static constexpr int nv(int) { return 0; }
+};
+
+}  // namespace pasif
