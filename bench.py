@@ -1,0 +1,360 @@
+#!/usr/bin/env python3
+"""bench.py -- fwd+adjoint gradient evals/s and RK4 system-steps/s of the hot path on N B200s (one JSON line).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3|c2|c5] [--impl reference]
+
+A "step" is one pass of the hot path over one batch: `getGradient` (checkpointed forward sweep + per-chunk recompute
++ adjoint sweep) for every (system x excitation) pair of the workload.  K forward-only passes (`getAmplitudes`) are
+timed in the same run and reported under "forward" (RK4 system-steps/s).
+
+  value   gradient evals/s with the excitation set already resident in HBM and the result left on the device,
+          timed with CUDA events on the engine's stream (sum of K steps), max over ranks.
+  e2e     the same metric through the C ABI with HOST buffers: every step uploads the excitation set
+          (pasif_load_excitations: H2D inside the timed region) and reads the [E][N_adj] result back to the host.
+  N > 1   weak scaling: every rank owns the full per-GPU workload (its own block of systems); the only collective is
+          one NCCL all-reduce(SUM) of the excitation-summed adjoint state per step, inside the timed region.
+
+Workloads (BASELINE.json configs):
+  c3 (default)  4096 jittered 8-state Gamma+Lambda systems x 64 excitations x 100 000 RK4 steps, fp32, fwd + adjoint
+                ("... on 1 B200", the single-GPU throughput configuration)
+  c2            1 system x 1024 excitations x 78 001 steps, fp64 (1024 trajectories: latency-, not throughput-bound)
+  c5            16384 systems x 64 excitations x 78 001 steps over 8 GPUs, fp64 -> 2048 systems per GPU
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    "c3": dict(n_systems=4096, E=64, L=100000, dtype="f32", jitter_seed=1, exc_seed=2,
+               name="C3: 4096 jittered 8-state Gamma+Lambda systems x 64 excitations x 100000 RK4 steps, fp32, forward + adjoint"),
+    "c2": dict(n_systems=1, E=1024, L=78001, dtype="f64", jitter_seed=None, exc_seed=0,
+               name="C2: 8-state Gamma+Lambda system x 1024 excitations x 78001 RK4 steps, fp64, forward + adjoint"),
+    "c5": dict(n_systems=2048, E=64, L=78001, dtype="f64", jitter_seed=4, exc_seed=2,
+               name="C5 shard: 2048 jittered 8-state systems x 64 excitations x 78001 RK4 steps per GPU, fp64, forward + adjoint"),
+}
+
+# algorithmic flops per trajectory-step of the 8-state system / 12-state Jacobian:
+#   D = 2 nnzK + 3 nnzG + 4 nnzL + 5 nnzP + 2 nnzF ; forward step 4 D + 13 N ; adjoint step 4 D_adj + 13 N_adj + 2 N
+F_FWD, F_BWD = 240.0, 380.0
+N_FWD, N_ADJ, N_NEEDED = 8, 12, 4
+
+
+def build_systems(w, rank):
+    from pasif_b200 import workloads as wl
+    if w["jitter_seed"] is None:
+        return [wl.fit8_system() for _ in range(w["n_systems"])], [wl.fit8_jacobian() for _ in range(w["n_systems"])]
+    rng = np.random.default_rng(w["jitter_seed"] + 1000 * rank)
+    systems = [wl.jitter(wl.fit8_system(), rng) for _ in range(w["n_systems"])]
+    jacs = [wl.fit8_jacobian() for _ in range(w["n_systems"])]
+    return systems, jacs
+
+
+def schedule(n, dtype):
+    """chunk schedule of the literal reference mode (reference src/__GpuDriver.cu:506-508)"""
+    t = np.float32 if dtype == "f32" else np.float64
+    nsp = int(np.sqrt(float(n)))
+    c = int(np.ceil(t(n) / t(nsp)))
+    return nsp, c
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self._stop = gpu, [], threading.Event()
+
+    def run(self):
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                       "-i", str(self.gpu)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.p.stdout:
+                self.rows.append([x.strip() for x in line.split(",")])
+                if self._stop.is_set():
+                    break
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop.set()
+        try:
+            self.p.terminate()
+        except Exception:
+            pass
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_baseline_sample(w, threads, seconds_target=15.0):
+    """The CPU oracle (C port of the reference's algorithm; the reference has no CPU path) on a bounded sample of the
+    same workload: a few systems x all excitations x a reduced step count.  Returns (gradient evals/s equivalent at the
+    workload's step count, forward system-steps/s, description)."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    from pasif_oracle_c import CRecordingDriver
+    from pasif_b200 import frontend, workloads as wl
+
+    class mod:
+        coo_tensor = frontend.coo_tensor
+
+    class D(CRecordingDriver):
+        dtype = np.float32 if w["dtype"] == "f32" else np.float64
+    n_sys = min(w["n_systems"], 2)
+    E = min(w["E"], 64)
+    steps = 4000
+    rng = np.random.default_rng(1)
+    systems = [wl.jitter(wl.fit8_system(), rng) for _ in range(n_sys)]
+    jacs = [wl.fit8_jacobian() for _ in range(n_sys)]
+    exc = wl.random_sine_excitations(E, steps, 16000, seed=w["exc_seed"])
+    p = frontend.make_frontend(D)([np.array(r) for r in exc], 16000, 0)
+    p._oracle.threads = threads
+    p.setSystems(*wl.to_frontend_args(systems, mod))
+    p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
+    t0 = time.time()
+    p.getAmplitudes()
+    t_f = time.time() - t0
+    t0 = time.time()
+    p.getGradient()
+    t_g = time.time() - t0
+    pairs = n_sys * E
+    grad_traj_steps_per_s = pairs * steps / t_g
+    return (grad_traj_steps_per_s / w["L"], pairs * steps / t_f,
+            f"{n_sys} systems x {E} excitations x {steps} steps ({w['dtype']}), C oracle, OpenMP {threads} threads; "
+            f"evals/s scaled to {w['L']} steps", t_f + t_g)
+
+
+def run_reference_arm(a, w):
+    """--impl reference: the reference ships no CPU implementation of this path, so this arm times
+    the oracle port -- a literal C restatement validated against the compiled reference's B200 outputs -- on the host
+    cores, each step one bounded sample of the workload."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    vals, fvals = [], []
+    sample = ""
+    for i in range(a.warmup + a.steps):
+        v, fv, sample, _ = cpu_baseline_sample(w, threads)
+        if i >= a.warmup:
+            vals.append(v)
+            fvals.append(fv)
+    value = float(np.mean(vals))
+    line = {"metric": "fwd+adjoint gradient evals/s", "value": value, "unit": "gradient evals/s", "n_gpus": a.gpus,
+            "steps": a.steps, "warmup": a.warmup, "ms_per_step": None, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic", "impl": "reference",
+            "config": {"workload": w["name"]},
+            "cpu_baseline": {"value": value, "unit": "gradient evals/s", "cores": threads, "kind": "port", "sample": sample},
+            "forward": {"metric": "RK4 system-steps/s", "value": float(np.mean(fvals)), "unit": "system-steps/s"},
+            "e2e": {"value": value, "unit": "gradient evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--systems", type=int, default=0, help="override the number of systems per GPU (debug)")
+    ap.add_argument("--length", type=int, default=0, help="override the number of RK4 steps (debug)")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    a = ap.parse_args()
+    w = dict(WORKLOADS[a.workload])
+    if a.systems:
+        w["n_systems"] = a.systems
+    if a.length:
+        w["L"] = a.length
+    if a.systems or a.length:
+        w["name"] += f" [override: {w['n_systems']} systems, {w['L']} steps]"
+    if a.impl == "reference":
+        return run_reference_arm(a, w)
+
+    import torch
+    from pasif_b200 import capi, frontend, workloads as wl
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    dist = None
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+
+    class mod:
+        coo_tensor = frontend.coo_tensor
+
+    S, E, L = w["n_systems"], w["E"], w["L"]
+    systems, jacs = build_systems(w, rank)
+    exc = np.ascontiguousarray(wl.random_sine_excitations(E, L, 16000, seed=w["exc_seed"]))
+    P = frontend.make_frontend(capi.engine_class(w["dtype"]))
+
+    class Local(P):
+        pass
+    import pasif_b200.frontend as fe
+    saved = fe._local_rank
+    fe._local_rank = lambda: local_rank
+    p = Local(exc, 16000, 0)
+    fe._local_rank = saved
+    t_setup = time.time()
+    p.setSystems(*wl.to_frontend_args(systems, mod))
+    p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
+    t_setup = time.time() - t_setup
+    p._setOption("profile", "on")
+    tdt = torch.float32 if w["dtype"] == "f32" else torch.float64
+    red = torch.zeros(world * S * N_ADJ, dtype=tdt, device=f"cuda:{local_rank}")
+    my = red[rank * S * N_ADJ:(rank + 1) * S * N_ADJ]
+
+    def barrier():
+        torch.cuda.synchronize()
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def grad_step_resident():
+        if dist is None:
+            p._getGradient(0, fetch=False)
+            return p._query("last_device_ms")
+        p._getGradientReducedDevice(my.data_ptr(), 0)
+        ms = p._query("last_device_ms")
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        dist.all_reduce(red)
+        ev1.record()
+        torch.cuda.synchronize()
+        return ms + ev0.elapsed_time(ev1)
+
+    pairs = S * E
+    # ---------------- warm-up (>= 3), then K timed gradient steps with resident inputs
+    for _ in range(max(a.warmup, 3)):
+        grad_step_resident()
+        p._getAmplitudes(fetch=False)
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    barrier()
+    wall0 = time.time()
+    dev_ms, k_ms = 0.0, {"gfwd": 0.0, "bwd": 0.0}
+    k_launch = {"gfwd": 0, "bwd": 0}
+    launches = 0
+    for _ in range(a.steps):
+        dev_ms += grad_step_resident()
+        launches += int(p._query("last_launches"))
+        for k in k_ms:
+            k_ms[k] += p._query("ms_" + k)
+            k_launch[k] += int(p._query("launches_" + k))
+    barrier()
+    wall_grad = time.time() - wall0
+    # ---------------- K forward-only passes (RK4 system-steps/s)
+    fwd_ms = 0.0
+    for _ in range(a.steps):
+        p._getAmplitudes(fetch=False)
+        fwd_ms += p._query("last_device_ms")
+        launches += int(p._query("last_launches"))
+    barrier()
+    clocks = sampler.stop()
+    # ---------------- e2e: host buffers in, host result out, every step
+    e2e_t = 0.0
+    for i in range(1 + a.steps):
+        barrier()
+        t0 = time.time()
+        p._loadExcitationsSet(exc, 16000)
+        g = p._getGradient(0)
+        if dist is not None:
+            dist.all_reduce(red)
+            torch.cuda.synchronize()
+        if i > 0:
+            e2e_t += time.time() - t0
+    tmax = torch.tensor([dev_ms, fwd_ms, e2e_t, wall_grad], dtype=torch.float64, device=f"cuda:{local_rank}")
+    if dist is not None:
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    dev_ms, fwd_ms, e2e_t, wall_grad = [float(x) for x in tmax.tolist()]
+    if rank != 0:
+        if dist is not None:
+            dist.destroy_process_group()
+        return
+
+    tot_pairs = pairs * world
+    value = tot_pairs * a.steps / (dev_ms * 1e-3)
+    fwd_value = tot_pairs * L * a.steps / (fwd_ms * 1e-3)
+    e2e_value = tot_pairs * a.steps / e2e_t
+    nsp, c = schedule(L, w["dtype"])
+    # literal reference schedule: forward sweep n steps + recompute (n - c) steps; adjoint (n - c) steps (chunk 0 skipped)
+    flops_gfwd = pairs * (2 * L - c) * F_FWD
+    flops_bwd = pairs * (L - c) * F_BWD
+    fma = {"f64": capi.fma_peak(local_rank, "f64"), "f32": capi.fma_peak(local_rank, "f32")}
+    peak = fma[w["dtype"]]
+    per_kernel = {}
+    for k, fl in (("gfwd", flops_gfwd), ("bwd", flops_bwd)):
+        t = k_ms[k] / a.steps * 1e-3
+        per_kernel[k] = {"tflops": fl / t / 1e12 if t > 0 else None, "ms_per_step": k_ms[k] / a.steps,
+                         "launches_per_step": k_launch[k] // a.steps,
+                         "avg_launch_ms": k_ms[k] / max(k_launch[k], 1)}
+    dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
+    sz = 4 if w["dtype"] == "f32" else 8
+    # chunk-trajectory traffic: needed forward variables written once (recompute) and read once (adjoint)
+    hbm_bytes = pairs * (L - c) * 2 * N_NEEDED * sz + pairs * nsp * N_FWD * sz * 2
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    line = {
+        "metric": "fwd+adjoint gradient evals/s", "value": value, "unit": "gradient evals/s", "n_gpus": world,
+        "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
+        "config": {"workload": w["name"], "systems_per_gpu": S, "excitations": E, "rk4_steps": L, "compat": "reference",
+                   "l2": "working set (checkpoints + chunk trajectory, > 1 GB) exceeds the 126 MB L2; no flush needed",
+                   "timing": "CUDA events on the engine stream, summed over the timed steps, max over ranks",
+                   "setup_s": t_setup},
+        "forward": {"metric": "RK4 system-steps/s", "value": fwd_value, "unit": "system-steps/s",
+                    "ms_per_step": fwd_ms / a.steps,
+                    "roofline": {"bound": "fma", "achieved": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12,
+                                 "peak": peak, "unit": "TFLOP/s",
+                                 "frac": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12 / peak}},
+        "roofline": {"bound": "fma", "kernel": {"gfwd": "pasif_gfwd_*", "bwd": "pasif_bwd_*"}[dom],
+                     "achieved": per_kernel[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
+                     "frac": per_kernel[dom]["tflops"] / peak if per_kernel[dom]["tflops"] else None, "traffic": None,
+                     "peak_source": "pasif_fma_peak register-resident FMA microbenchmark, same run (MEASURED_PEAKS.json has no FMA-pipe figure)",
+                     "whole_step": {"achieved": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12,
+                                    "frac": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12 / peak},
+                     "per_kernel": per_kernel, "fma_peak_tflops": fma},
+        "roofline_hbm": {"bound": "hbm", "achieved": hbm_bytes / (dev_ms / a.steps * 1e-3) / 1e9, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": hbm_bytes / (dev_ms / a.steps * 1e-3) / 1e9 / hbm_peak,
+                         "note": "algorithmic chunk-trajectory + checkpoint bytes of the whole gradient step over its device time",
+                         "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
+        "e2e": {"value": e2e_value, "unit": "gradient evals/s", "h2d_bytes_per_step": int(exc.nbytes),
+                "d2h_bytes_per_step": int(pairs * N_ADJ * sz), "host_buffers": "pageable numpy arrays through the C ABI"},
+        "gpu_launches": launches, "clocks": clocks, "wall_s_grad_steps": wall_grad,
+    }
+    if not a.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        v, fv, sample, _ = cpu_baseline_sample(w, threads)
+        line["cpu_baseline"] = {"value": v, "unit": "gradient evals/s", "cores": threads, "kind": "port", "sample": sample,
+                                "forward_system_steps_per_s": fv}
+    print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -20,6 +20,16 @@ import math
 import numpy as np
 
 
+def update_slope(q, m, dt):
+    """`updateSlope` kernel (reference src/kernels.cu:201-210): rki = q + dt * rk."""
+    return q + dt * m
+
+
+def integrate(q, m1, m2, m3, m4, h6):
+    """`integrate` kernel (reference src/kernels.cu:218-229): q += h6 * (rk1 + 2 rk2 + 2 rk3 + rk4)."""
+    return q + h6 * (m1 + 2 * m2 + 2 * m3 + m4)
+
+
 class _Tensor:
     """COO tensor of order 3/4/5 as handed over by the front end: flat indices [out, in1, in2, ...] per nnz
     (reference `src/helpers.cu:266-652`; index roles from `src/kernels.cu:52,56,61`)."""
@@ -141,16 +151,16 @@ class PasifOracle:
         h, h2, h6 = self.h, self.h2, self.h6
         m1 = self._deriv(s, Q, Q)
         self._force(m1, step, False)
-        mi = Q + h2 * m1
+        mi = update_slope(Q, m1, h2)
         m2 = self._deriv(s, mi, mi)
         self._force(m2, step, True)
-        mi = Q + h2 * m2
+        mi = update_slope(Q, m2, h2)
         m3 = self._deriv(s, mi, mi)
         self._force(m3, step, True)
-        mi = Q + h * m3
+        mi = update_slope(Q, m3, h)
         m4 = self._deriv(s, mi, mi)
         self._force(m4, step + 1, False)
-        return Q + h6 * (m1 + 2 * m2 + 2 * m3 + m4)
+        return integrate(Q, m1, m2, m3, m4, h6)
 
     def _ic(self, s):
         return np.tile(s.IC[None, :], (self.E, 1)).astype(self.dtype)     # extendTheVector, src/helpers.cu:808-816
@@ -182,13 +192,13 @@ class PasifOracle:
         s = self.bwd
         h, h2, h6 = self.h, self.h2, self.h6
         m1 = self._deriv(s, lam, q_a)
-        mi = lam + h2 * m1
+        mi = update_slope(lam, m1, h2)
         m2 = self._deriv(s, mi, q_half)
-        mi = lam + h2 * m2
+        mi = update_slope(lam, m2, h2)
         m3 = self._deriv(s, mi, q_half)
-        mi = lam + h * m3
+        mi = update_slope(lam, m3, h)
         m4 = self._deriv(s, mi, q_b)
-        return lam + h6 * (m1 + 2 * m2 + 2 * m3 + m4)
+        return integrate(lam, m1, m2, m3, m4, h6)
 
     def schedule(self):
         """numSetpoints / chunkSize / lastChunkSize exactly as src/__GpuDriver.cu:506-508 (reel arithmetic)."""
@@ -268,10 +278,12 @@ class RecordingDriver:
     forwards solver calls to a PasifOracle.  `dtype` class attribute selects the emulated `reel`."""
     dtype = np.float64
     compat = "reference"
+    oracle_cls = None      # default: PasifOracle (NumPy); pasif_oracle_c.CRecordingDriver swaps in the C oracle
 
     def __init__(self, excitationSet_, sampleRate_, numsteps_, dCompute_=False, dSystem_=False, dSolver_=False, GPUId_=0):
         self.rec = {}
-        self._oracle = PasifOracle(np.asarray(excitationSet_, dtype=np.float64), sampleRate_, numsteps_, self.dtype)
+        cls = self.oracle_cls or PasifOracle
+        self._oracle = cls(np.asarray(excitationSet_, dtype=np.float64), sampleRate_, numsteps_, self.dtype)
         self._psi_f = None
         self._psi_b = None
 

@@ -29,6 +29,12 @@
 #endif
 
 #define PASIF_DEV __device__ __forceinline__
+// constexpr index table: after full unrolling the argument is a literal and the call folds to a constant
+#define PASIF_TAB(name, ...)                       \
+  PASIF_DEV static constexpr int name(int k) {     \
+    constexpr int a[] = {__VA_ARGS__};             \
+    return a[k];                                   \
+  }
 
 namespace pasif {
 
