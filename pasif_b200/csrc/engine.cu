@@ -326,14 +326,16 @@ struct pasif_engine {
   std::vector<DevClass> fwd_classes, joint_classes;
   bool fwd_ready = false, joint_ready = false;
   bool exc_dirty = true;
-  DevBuf d_exc, d_user, d_traj, d_ckpt, d_dense, d_lam, d_red;
+  DevBuf d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;
   long long exc_rows = 0;
   bool exc_half = false;
-  cudaStream_t stream = nullptr;
+  cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: adjoint sweep of chunk k overlaps the recompute of chunk k-1
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
+  bool overlap = true;
   std::string err;
   bool compat_clean = false, jit_on = true;
-  int block = PASIF_BLOCK;
+  int block = PASIF_BLOCK, n_sm = 148;
   double last_ms = 0;
   long long last_launches = 0, jit_compiles = 0, aot_hits = 0, jit_cache_hits = 0;
   // option profile=on: CUDA-event pair around every hot-kernel launch, summed per kind (0 fwd, 1 gradient-fwd, 2 bwd)
@@ -473,17 +475,26 @@ cudaEvent_t prof_event(pasif_engine& E, int kind) {
   return E.prof_events[E.prof_used++];
 }
 
+// threads per CTA: the configured maximum while the grid still gives every SM >= 2 CTAs, else narrower CTAs so that
+// a small batch (config C2: 1024 trajectories) spreads over more SMs
+unsigned pick_block(const pasif_engine& E, long long n_threads) {
+  unsigned block = (unsigned)E.block;
+  while (block > 32 && (n_threads + block - 1) / block < 2ll * E.n_sm) block >>= 1;
+  return block < 32 ? 32 : block;
+}
+
 template <typename Args>
-void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& args, int kind) {
+void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& args, int kind, cudaStream_t st = nullptr) {
   if (!k.valid()) throw std::runtime_error("internal: kernel handle not resolved");
-  const unsigned block = (unsigned)E.block;
+  if (!st) st = E.stream;
+  const unsigned block = pick_block(E, n_threads);
   const unsigned grid = (unsigned)((n_threads + block - 1) / block);
   void* params[] = {(void*)&args};
-  if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), E.stream));
-  if (k.aot) CUDA_CHECK(cudaLaunchKernel(k.aot, dim3(grid), dim3(block), params, 0, E.stream));
-  else if (g_drv.LaunchKernel(k.jit, grid, 1, 1, block, 1, 1, 0, (CUstream)E.stream, params, nullptr) != CUDA_SUCCESS)
+  if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), st));
+  if (k.aot) CUDA_CHECK(cudaLaunchKernel(k.aot, dim3(grid), dim3(block), params, 0, st));
+  else if (g_drv.LaunchKernel(k.jit, grid, 1, 1, block, 1, 1, 0, (CUstream)st, params, nullptr) != CUDA_SUCCESS)
     throw std::runtime_error("cuLaunchKernel failed");
-  if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), E.stream));
+  if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), st));
   ++E.last_launches;
   ++E.kind_launches[kind];
 }
@@ -716,22 +727,37 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         launch(E, c.k_gfwd, P, a, 1);
       }
       const long long first = E.compat_clean ? 0 : 1;      // the reference never back-propagates chunk 0 (quirk A2)
+      // Two streams, two chunk-trajectory buffers: the recompute of chunk k-1 (stream) runs while the adjoint sweep of
+      // chunk k (stream2) is still in flight, so the partial last wave of one kernel is filled by CTAs of the other.
+      // profile=on serialises them again (per-kernel CUDA-event times are only meaningful without co-running kernels).
+      const bool ovl = E.overlap && !E.profile;
+      if (ovl) E.d_dense2.reserve(std::max<size_t>((size_t)chunk * NV * P, 1) * sizeof(T));
+      T* dense_buf[2] = {(T*)E.d_dense.p, ovl ? (T*)E.d_dense2.p : (T*)E.d_dense.p};
+      cudaStream_t sB = ovl ? E.stream2 : E.stream;
+      long long it = 0;
+      int last_buf = -1;
       for (long long sp = nsp - 1; sp >= first; --sp) {
         const long long start = sp * chunk;
         const long long end = std::min<long long>(n, start + chunk);
         const long long len = end - start;
         if (len <= 0) continue;
+        const int buf = (int)(it & 1);
+        if (ovl && it >= 2) CUDA_CHECK(cudaStreamWaitEvent(E.stream, E.ev_bwd[buf], 0));   // buffer consumed
         pasif::FwdArgs<T> a;
         fill_common<T>(E, c, a);
         a.q_in = ckpt + (size_t)sp * slot_elems;
         a.t0 = (int)start; a.t1 = (int)end;
-        a.dense_ptr = (T*)E.d_dense.p;
-        launch(E, c.k_gfwd, P, a, 1);
+        a.dense_ptr = dense_buf[buf];
+        launch(E, c.k_gfwd, P, a, 1, E.stream);
+        if (ovl) {
+          CUDA_CHECK(cudaEventRecord(E.ev_rec[buf], E.stream));
+          CUDA_CHECK(cudaStreamWaitEvent(sB, E.ev_rec[buf], 0));
+        }
         pasif::BwdArgs<T> b;
         std::memset(&b, 0, sizeof b);
         b.coef = (const T*)c.coef_adj.p;
         b.lam = (T*)E.d_lam.p;
-        b.dense = (const T*)E.d_dense.p;
+        b.dense = dense_buf[buf];
         // state standing in for index -1: the reference reads the PREVIOUS chunk's checkpoint slot (quirk A4);
         // the exact sweep uses this chunk's own start state
         b.prev = ckpt + (size_t)(E.compat_clean ? sp : sp - 1) * slot_elems;
@@ -739,9 +765,13 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         b.alias_local = E.compat_clean ? -1000000 : (int)(S_global - sp);
         b.n_inst = c.h.n_inst; b.E = (int)E.E; b.n_traj = (int)P;
         b.h = a.h; b.h2 = a.h2; b.h6 = a.h6;
-        launch(E, c.k_bwd, P, b, 2);
+        launch(E, c.k_bwd, P, b, 2, sB);
+        if (ovl) CUDA_CHECK(cudaEventRecord(E.ev_bwd[buf], sB));
+        last_buf = buf;
+        ++it;
         if (!E.compat_clean && sp == (long long)save) break;
       }
+      if (ovl && last_buf >= 0) CUDA_CHECK(cudaStreamWaitEvent(E.stream, E.ev_bwd[last_buf], 0));
     }
     const long long tot = (long long)NA * P;
     scatter_user_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
@@ -843,7 +873,13 @@ int pasif_create(pasif_engine** out, const double* excitations, uint32_t n_excit
                                  "): pasif_b200 has no CPU fallback");
       if (device >= count) throw std::runtime_error("GPU id " + std::to_string(device) + " out of range");
       CUDA_CHECK(cudaSetDevice(device));
+      CUDA_CHECK(cudaDeviceGetAttribute(&e->n_sm, cudaDevAttrMultiProcessorCount, device));
       CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking));
+      CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+      for (int i = 0; i < 2; ++i) {
+        CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));
+        CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_bwd[i], cudaEventDisableTiming));
+      }
       CUDA_CHECK(cudaEventCreate(&e->ev0));
       CUDA_CHECK(cudaEventCreate(&e->ev1));
     }
@@ -862,7 +898,12 @@ void pasif_destroy(pasif_engine* e) {
     cudaSetDevice(e->device);
     free_classes(e->fwd_classes);
     free_classes(e->joint_classes);
-    for (DevBuf* b : {&e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_lam, &e->d_red}) b->release();
+    for (DevBuf* b : {&e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
+    for (int i = 0; i < 2; ++i) {
+      if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
+      if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
+    }
+    if (e->stream2) cudaStreamDestroy(e->stream2);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -958,6 +999,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     int b = std::atoi(v.c_str());
     if (b < 32 || b > PASIF_BLOCK || (b & 31)) throw std::runtime_error("block must be a multiple of 32 in [32, " + std::to_string(PASIF_BLOCK) + "]");
     e->block = b;
+  } else if (k == "overlap") {
+    e->overlap = (v == "on" || v == "1");
   } else if (k == "profile") {
     e->profile = (v == "on" || v == "1");
   } else if (k == "numsteps") {
