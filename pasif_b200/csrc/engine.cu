@@ -26,6 +26,7 @@
 #include "../../include/pasif_b200.h"
 #include "pattern.hpp"
 #include "rk4_kernels.cuh"
+#include "large_kernels.cuh"
 
 using namespace pasif_host;
 
@@ -305,8 +306,12 @@ struct DevBuf {
   }
 };
 
+struct LargeClass;
+struct LargeClassDeleter { void operator()(LargeClass* p) const; };
+
 struct DevClass {
   ClassData h;
+  std::unique_ptr<LargeClass, LargeClassDeleter> large;   // set for components beyond the register-resident range
   DevBuf coef, ic, varmap, coef_adj, ic_adj, varmap_adj;
   KernelHandle k_fwd, k_gfwd, k_bwd;
   CUmodule module = nullptr;
@@ -334,7 +339,9 @@ struct pasif_engine {
   cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
   bool overlap = true;
   std::string err;
-  bool compat_clean = false, jit_on = true;
+  bool compat_clean = false, jit_on = true, gemm_on = true;
+  int large_threshold = 48;                      // components with more coupled variables use the tile kernels
+  long long large_classes = 0, large_gemm_classes = 0;
   int block = PASIF_BLOCK, n_sm = 148;
   double last_ms = 0;
   long long last_launches = 0, jit_compiles = 0, aot_hits = 0, jit_cache_hits = 0;
@@ -503,9 +510,20 @@ void free_classes(std::vector<DevClass>& v) {
   for (auto& c : v) {
     c.coef.release(); c.ic.release(); c.varmap.release();
     c.coef_adj.release(); c.ic_adj.release(); c.varmap_adj.release();
+    c.large.reset();
     if (c.module && g_drv.ok) g_drv.ModuleUnload(c.module);
   }
   v.clear();
+}
+
+template <typename T>
+void build_large_class(pasif_engine& E, DevClass& dc);
+template <typename T>
+void large_solve_forward(pasif_engine& E, DevClass& c, bool trajectory, uint32_t save_steps, uint64_t n_slots);
+template <typename T>
+void large_solve_gradient(pasif_engine& E, DevClass& c, uint32_t save, T* d_user_out);
+bool is_large(const pasif_engine& E, const ClassData& c) {
+  return std::max(c.fwd.N, c.adj.N) > E.large_threshold || c.fwd.nc() + c.adj.nc() > 2048;
 }
 
 template <typename T>
@@ -526,7 +544,8 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
       upload<T>(dc.ic_adj, dc.h.ic_adj);
       upload_int(dc.varmap_adj, dc.h.varmap_adj);
     }
-    resolve_kernels(E, dc);
+    if (is_large(E, dc.h)) build_large_class<T>(E, dc);
+    else resolve_kernels(E, dc);
   }
 }
 
@@ -653,6 +672,7 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
   }
   begin_timing(E);
   for (DevClass& c : E.fwd_classes) {
+    if (c.large) { large_solve_forward<T>(E, c, trajectory, save_steps, n_slots); continue; }
     pasif::FwdArgs<T> a;
     fill_common<T>(E, c, a);
     a.t0 = 0; a.t1 = (int)E.numsteps;
@@ -681,11 +701,17 @@ Schedule reference_schedule(uint32_t n) {       // reference src/__GpuDriver.cu:
   return s;
 }
 
+#include "large_host.inc"
+void LargeClassDeleter::operator()(LargeClass* p) const {
+  if (p) { p->release(); delete p; }
+}
+
 template <typename T>
 void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
   const long long n = E.numsteps;
   const int threads = 256;
   for (DevClass& c : E.joint_classes) {
+    if (c.large) { large_solve_gradient<T>(E, c, save, d_user_out); continue; }
     const long long P = c.n_traj;
     const int NF = c.h.fwd.N, NA = c.h.adj.N, NV = (int)c.h.adj.nv.size();
     E.d_lam.reserve((size_t)NA * P * sizeof(T));
@@ -999,6 +1025,10 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     int b = std::atoi(v.c_str());
     if (b < 32 || b > PASIF_BLOCK || (b & 31)) throw std::runtime_error("block must be a multiple of 32 in [32, " + std::to_string(PASIF_BLOCK) + "]");
     e->block = b;
+  } else if (k == "gemm") {
+    e->gemm_on = (v == "on" || v == "1");
+  } else if (k == "large_threshold") {
+    e->large_threshold = std::atoi(v.c_str());
   } else if (k == "overlap") {
     e->overlap = (v == "on" || v == "1");
   } else if (k == "profile") {
@@ -1069,6 +1099,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "jit_cache_hits") *value = (double)e->jit_cache_hits;
   else if (k == "aot_hits") *value = (double)e->aot_hits;
   else if (k == "dtype") *value = e->dtype;
+  else if (k == "large_classes") *value = (double)e->large_classes;
+  else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "aot_table_size") *value = (double)aot_table().size();
   else if (k == "ms_fwd") *value = e->kind_ms[0];
   else if (k == "ms_gfwd") *value = e->kind_ms[1];

@@ -119,6 +119,60 @@ def fit8_jacobian():
                 Psi=([A, A, S, S, S], [1.], [1, 1, 1, 1, 1]))
 
 
+def chain_system(ndof, dense=False, seed=3, k=2.0e4, b=8.0, g=40.0, lam=3.0e5, F0=2.0e4):
+    """BASELINE config 4: one `ndof`-DOF oscillator chain, state [x_0..x_{n-1}, v_0..v_{n-1}, p2, p1] (N = 2 ndof + 2):
+    m_i v_i' = -(K x)_i - (B v)_i - g_i x_i^2 - lam_i x_i^3 + F_i e(t),  x_i' = v_i,  p1' = x_0^2,  p2' = p1
+    (the probe pair of examples/FullInterfaceTesting_1dof.py:68-70).  sparse: K tridiagonal (nearest-neighbour springs,
+    fixed ends), B diagonal.  dense: K, B random symmetric positive definite with the same spectral scale, so the
+    pre-scaled linear operator K' has ~50 % non-zeros and is shared by every excitation replica."""
+    rng = np.random.default_rng(seed)
+    n = int(ndof)
+    N = 2 * n + 2
+    p2, p1 = 2 * n, 2 * n + 1
+    M = np.ones(N)
+    M[n:2 * n] = rng.uniform(0.8, 1.25, size=n)
+    bv, br, bc = [-1.0] * n + [-1.0], list(range(n)) + [p2], list(range(n, 2 * n)) + [p1]      # x' = v, p2' = p1
+    kv, kr, kc = [], [], []
+    if not dense:
+        ks = k * rng.uniform(0.8, 1.25, size=n + 1)                                   # springs between neighbours / walls
+        for i in range(n):
+            kv.append(ks[i] + ks[i + 1]); kr.append(n + i); kc.append(i)
+            if i > 0:
+                kv.append(-ks[i]); kr.append(n + i); kc.append(i - 1)
+            if i < n - 1:
+                kv.append(-ks[i + 1]); kr.append(n + i); kc.append(i + 1)
+        for i in range(n):
+            bv.append(b * rng.uniform(0.8, 1.25)); br.append(n + i); bc.append(n + i)
+    else:
+        A = rng.standard_normal((n, n)) / np.sqrt(n)
+        Kd = k * (A @ A.T + 0.5 * np.eye(n))
+        C = rng.standard_normal((n, n)) / np.sqrt(n)
+        Bd = b * (C @ C.T + 0.5 * np.eye(n))
+        for i in range(n):
+            for j in range(n):
+                kv.append(Kd[i, j]); kr.append(n + i); kc.append(j)
+                bv.append(Bd[i, j]); br.append(n + i); bc.append(n + j)
+    gval, gidx = [-1.0], [p1, 0, 0]
+    lval, lidx = [], []
+    for i in range(n):
+        gval.append(g * rng.uniform(0.5, 1.5)); gidx += [n + i, i, i]
+        lval.append(lam * rng.uniform(0.5, 1.5)); lidx += [n + i, i, i, i]
+    F = np.zeros(N)
+    F[n:2 * n] = F0 * rng.uniform(0.2, 1.0, size=n)
+    return _sys(N, M, (bv, br, bc), (kv, kr, kc), ([N] * 3, gval, gidx), ([N] * 4, lval, lidx), F, np.zeros(N))
+
+
+def chain_jacobian(system, n_params=4):
+    """Adjoint system of `chain_system` for the loss p1(T) = int x_0^2 dt with gradients w.r.t. the first `n_params`
+    on-site cubic coefficients (pasif_b200.adjoint.build_adjoint)."""
+    from .adjoint import build_adjoint
+    N = system["n"]
+    loss = np.zeros(N)
+    loss[N - 1] = 1.0
+    nl = len(system["Lambda"][1])
+    return build_adjoint(system, loss, [("Lambda", k) for k in range(min(n_params, nl))])
+
+
 def jitter(system, rng, rel=0.1):
     """Copy of ``system`` whose B/K/Gamma/Lambda/Psi/F values are scaled by independent U(1-rel, 1+rel)."""
     s = copy.deepcopy(system)

@@ -1,0 +1,96 @@
+"""GPU suite for the LARGE-component path (shared-memory tile kernels, pasif_b200/csrc/large_kernels.cuh), called
+through the C ABI:
+  * the reference's golden vectors again, with every component forced through the tile kernels (large_threshold=0);
+  * oscillator chains (BASELINE config 4 shape, scaled down) against the C oracle: sparse row programs and the
+    tensor-core GEMM path (dense shared K'), forward + trajectory + adjoint, both schedules, both precisions;
+  * several instances with their own coefficients, ragged tiles (E not a multiple of the tile width).
+Tolerances as in test_parity_gpu.py (fp64 <= 1e-12 per variable; fp32 <= 1e-5 forward / 5e-5 adjoint on the vector)."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err, col_err, run_case
+from pasif_b200 import capi, workloads as wl
+from pasif_oracle_c import CRecordingDriver
+
+pytestmark = pytest.mark.gpu
+
+TOL_FWD = {"f64": 1e-12, "f32": 1e-5}
+TOL_ADJ = {"f64": 1e-12, "f32": 5e-5}
+FORCE_LARGE = {"large_threshold": "0"}
+
+
+def _oracle(prec, compat):
+    class D(CRecordingDriver):
+        dtype = np.float64 if prec == "f64" else np.float32
+    D.compat = compat
+    return D
+
+
+def close(a, b, width, prec, tol):
+    if prec == "f64":
+        return col_err(a, b, width) < tol[prec]
+    return rel_err(a, b) < tol[prec] and col_err(a, b, width) < 2e-3
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["mixed2", "fit8x2_jit", "ex1dof_short", "ex1dof_sq", "ex1dof_interp", "fit8_e16"])
+def test_tile_kernels_match_reference_golden(name, prec):
+    z = golden(name, prec)
+    case = wl.golden_case(name)
+    out = run_case(capi.engine_class(prec), case, options=FORCE_LARGE)
+    assert out["_p"]._query("large_classes") >= 1
+    E = len(case["excitations"])
+    assert close(out["amplitudes"], z["amplitudes"], z["amplitudes"].size // E, prec, TOL_FWD)
+    assert np.array_equal(out["amplitudes"], out["amplitudes_2nd"])
+    if "trajectory" in z.files:
+        assert out["trajectory"].shape == z["trajectory"].shape
+        assert rel_err(out["trajectory"][1:], z["trajectory"][1:]) < TOL_FWD[prec]
+    if "gradient" in z.files:
+        assert close(out["gradient"], z["gradient"], z["gradient"].size // E, prec, TOL_ADJ)
+
+
+def chain_case(ndof, dense, E, L, n_sys=1, seed=3):
+    rng = np.random.default_rng(seed)
+    base = wl.chain_system(ndof, dense=dense, seed=seed)
+    systems = [base] if n_sys == 1 else [wl.jitter(base, rng, rel=0.05) for _ in range(n_sys)]
+    return dict(systems=systems, jacobians=[wl.chain_jacobian(s, 3) for s in systems],
+                excitations=wl.random_sine_excitations(E, L, 16000, seed=seed + 1), sample_rate=16000, numsteps=0,
+                interp=None, traj_save_steps=max(L // 7, 1))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("compat", ["reference", "clean"])
+@pytest.mark.parametrize("dense", [False, True])
+def test_chain_matches_oracle(dense, compat, prec):
+    case = chain_case(40, dense, E=11, L=700)
+    a = run_case(capi.engine_class(prec, compat), case)
+    b = run_case(_oracle(prec, compat), case)
+    assert a["_p"]._query("large_classes") >= 1
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+def test_gemm_path_is_used_and_agrees_with_row_programs():
+    """Dense shared K': the tensor-core path (DMMA) and the sparse row programs (gemm=off) give the same fp64 result."""
+    case = chain_case(48, True, E=16, L=400)
+    a = run_case(capi.engine_class("f64"), case)
+    b = run_case(capi.engine_class("f64"), case, options={"gemm": "off"})
+    assert a["_p"]._query("large_gemm_classes") >= 1 and b["_p"]._query("large_gemm_classes") == 0
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert col_err(a["amplitudes"], b["amplitudes"], n) < 1e-12
+    assert col_err(a["gradient"], b["gradient"], na) < 1e-12
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_several_chain_instances_ragged_tiles(prec):
+    case = chain_case(30, False, E=19, L=500, n_sys=3)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    n = sum(s["n"] for s in case["systems"])
+    na = sum(s["n"] for s in case["jacobians"])
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+    red = np.asarray(a["_p"]._getGradientReduced(0))
+    assert rel_err(red, a["gradient"].reshape(19, na).sum(axis=0)) < (1e-12 if prec == "f64" else 1e-5)
