@@ -42,6 +42,12 @@ WORKLOADS = {
                name="C2: 8-state Gamma+Lambda system x 1024 excitations x 78001 RK4 steps, fp64, forward + adjoint"),
     "c5": dict(n_systems=2048, E=64, L=78001, dtype="f64", jitter_seed=4, exc_seed=2,
                name="C5 shard: 2048 jittered 8-state systems x 64 excitations x 78001 RK4 steps per GPU, fp64, forward + adjoint"),
+    # config 4 (large-DOF shared-B batch): ONE 256-DOF chain (514 states, 518-state adjoint) x 16384 excitation replicas.
+    # The rate is step-count independent; the step counts keep a bench step at a few seconds.
+    "c4s": dict(kind="chain", dense=False, ndof=256, n_systems=1, E=16384, L=2000, dtype="f64", jitter_seed=None, exc_seed=5,
+                name="C4 sparse: 256-DOF oscillator chain (tridiagonal K, on-site Gamma/Lambda; 514 states) x 16384 excitations x 2000 RK4 steps, forward + adjoint (tile kernels, row programs)"),
+    "c4d": dict(kind="chain", dense=True, ndof=256, n_systems=1, E=16384, L=128, dtype="f64", jitter_seed=None, exc_seed=5,
+                name="C4 dense: 256-DOF system with dense shared K, B (514 states) x 16384 excitations x 128 RK4 steps, forward + adjoint (tile kernels, tensor-core linear term)"),
 }
 
 # algorithmic flops per trajectory-step of the 8-state system / 12-state Jacobian:
@@ -50,8 +56,24 @@ F_FWD, F_BWD = 240.0, 380.0
 N_FWD, N_ADJ, N_NEEDED = 8, 12, 4
 
 
+def system_work(s, j):
+    """(F_fwd, F_bwd, N_fwd, N_adj) of one system / Jacobian pair from their non-zero counts."""
+    def nnzk(d):
+        rows = list(map(int, d["B"][1])) + list(map(int, d["K"][1]))
+        cols = list(map(int, d["B"][2])) + list(map(int, d["K"][2]))
+        return len(set(zip(rows, cols)))
+
+    def D(d, force):
+        return (2 * nnzk(d) + 3 * len(d["Gamma"][1]) + 4 * len(d["Lambda"][1]) + 5 * len(d.get("Psi", ([], [], []))[1])
+                + (2 * int(np.count_nonzero(d["F"])) if force else 0))
+    return (4.0 * D(s, True) + 13 * s["n"], 4.0 * D(j, False) + 13 * j["n"] + 2 * s["n"], s["n"], j["n"])
+
+
 def build_systems(w, rank):
     from pasif_b200 import workloads as wl
+    if w.get("kind") == "chain":
+        s = wl.chain_system(w["ndof"], dense=w["dense"])
+        return [s], [wl.chain_jacobian(s, 4)]
     if w["jitter_seed"] is None:
         return [wl.fit8_system() for _ in range(w["n_systems"])], [wl.fit8_jacobian() for _ in range(w["n_systems"])]
     rng = np.random.default_rng(w["jitter_seed"] + 1000 * rank)
@@ -119,12 +141,19 @@ def cpu_baseline_sample(w, threads, seconds_target=15.0):
 
     class D(CRecordingDriver):
         dtype = np.float32 if w["dtype"] == "f32" else np.float64
-    n_sys = min(w["n_systems"], 2)
-    E = min(w["E"], 64)
-    steps = 4000
-    rng = np.random.default_rng(1)
-    systems = [wl.jitter(wl.fit8_system(), rng) for _ in range(n_sys)]
-    jacs = [wl.fit8_jacobian() for _ in range(n_sys)]
+    if w.get("kind") == "chain":
+        n_sys, E = 1, min(w["E"], 4 * threads)
+        steps = 40 if w["dense"] else 400
+        systems, jacs = build_systems(w, 0)
+        what = w["name"].split(":")[0]
+    else:
+        n_sys = min(w["n_systems"], 16)
+        E = min(w["E"], 64)
+        steps = w["L"]                         # full length: ~10 s of work on 16 host cores
+        rng = np.random.default_rng(1)
+        systems = [wl.jitter(wl.fit8_system(), rng) for _ in range(n_sys)]
+        jacs = [wl.fit8_jacobian() for _ in range(n_sys)]
+        what = f"{n_sys} systems"
     exc = wl.random_sine_excitations(E, steps, 16000, seed=w["exc_seed"])
     p = frontend.make_frontend(D)([np.array(r) for r in exc], 16000, 0)
     p._oracle.threads = threads
@@ -139,8 +168,31 @@ def cpu_baseline_sample(w, threads, seconds_target=15.0):
     pairs = n_sys * E
     grad_traj_steps_per_s = pairs * steps / t_g
     return (grad_traj_steps_per_s / w["L"], pairs * steps / t_f,
-            f"{n_sys} systems x {E} excitations x {steps} steps ({w['dtype']}), C oracle, OpenMP {threads} threads; "
+            f"{what} x {E} excitations x {steps} steps ({w['dtype']}), C oracle, OpenMP {threads} threads; "
             f"evals/s scaled to {w['L']} steps", t_f + t_g)
+
+
+def reference_gpu_sample(w):
+    """The reference's own (GPU) implementation, unmodified, on the same B200: oracle/time_reference_gpu.py in a
+    subprocess.  Reported beside the CPU figures; None when no GPU / no compiled reference / not an 8-state workload."""
+    so = os.path.join(ROOT, "oracle", "_ref", w["dtype"], "PASIfgpu.so")
+    if w.get("kind") == "chain" or not os.path.exists(so):
+        return None
+    try:
+        if subprocess.run(["nvidia-smi", "-L"], capture_output=True, timeout=30).returncode != 0:
+            return None
+        S, E, steps = min(w["n_systems"], 2), min(w["E"], 64), 20000
+        r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference_gpu.py"), "--prec", w["dtype"],
+                            "--systems", str(S), "--excitations", str(E), "--steps", str(steps), "--exc-seed", str(w["exc_seed"])],
+                           capture_output=True, text=True, timeout=600)
+        d = json.loads(r.stdout.strip().splitlines()[-1])
+        return {"value": d["gradient_trajectory_steps_per_s"] / w["L"], "unit": "gradient evals/s",
+                "forward_system_steps_per_s": d["forward_system_steps_per_s"], "gradient_s": d["gradient_s"], "forward_s": d["forward_s"],
+                "sample": f"unmodified reference (sm_100 build of src/*.cu, {w['dtype']}) through its own PASIf.py on this GPU: {S} systems x {E} "
+                          f"excitations x {steps} steps (its front end cannot assemble more than 2 Jacobians; its per-step cost is "
+                          f"launch-bound, i.e. independent of the batch at this size); evals/s scaled to {w['L']} steps"}
+    except Exception as e:  # noqa
+        return {"unavailable": repr(e)[:200]}
 
 
 def run_reference_arm(a, w):
@@ -167,6 +219,9 @@ def run_reference_arm(a, w):
             "forward": {"metric": "RK4 system-steps/s", "value": float(np.mean(fvals)), "unit": "system-steps/s"},
             "e2e": {"value": value, "unit": "gradient evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
+    rg = reference_gpu_sample(w)
+    if rg is not None:
+        line["reference_gpu"] = rg
     print(json.dumps(line))
 
 
@@ -179,6 +234,8 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--systems", type=int, default=0, help="override the number of systems per GPU (debug)")
     ap.add_argument("--length", type=int, default=0, help="override the number of RK4 steps (debug)")
+    ap.add_argument("--dtype", default="", choices=["", "f32", "f64"], help="override the workload's compute type")
+    ap.add_argument("--excitations", type=int, default=0, help="override the number of excitations (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
@@ -186,8 +243,13 @@ def main():
         w["n_systems"] = a.systems
     if a.length:
         w["L"] = a.length
-    if a.systems or a.length:
-        w["name"] += f" [override: {w['n_systems']} systems, {w['L']} steps]"
+    if a.excitations:
+        w["E"] = a.excitations
+    if a.systems or a.length or a.excitations:
+        w["name"] += f" [override: {w['n_systems']} systems, {w['E']} excitations, {w['L']} steps]"
+    if a.dtype:
+        w["dtype"] = a.dtype
+        w["name"] += f" [{a.dtype}]"
     if a.impl == "reference":
         return run_reference_arm(a, w)
 
@@ -209,6 +271,12 @@ def main():
 
     S, E, L = w["n_systems"], w["E"], w["L"]
     systems, jacs = build_systems(w, rank)
+    global F_FWD, F_BWD, N_FWD, N_ADJ, N_NEEDED
+    F_FWD, F_BWD, N_FWD, N_ADJ = system_work(systems[0], jacs[0])
+    large = w.get("kind") == "chain"
+    # forward variables written once (recompute) and read once (adjoint): the needed ones (register path) or all rows
+    # padded to 32 (tile path)
+    N_NEEDED = (N_FWD + 31) // 32 * 32 if large else 4
     exc = np.ascontiguousarray(wl.random_sine_excitations(E, L, 16000, seed=w["exc_seed"]))
     P = frontend.make_frontend(capi.engine_class(w["dtype"]))
 
@@ -324,7 +392,7 @@ def main():
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     sz = 4 if w["dtype"] == "f32" else 8
     # chunk-trajectory traffic: needed forward variables written once (recompute) and read once (adjoint)
-    hbm_bytes = pairs * (L - c) * 2 * N_NEEDED * sz + pairs * nsp * N_FWD * sz * 2
+    hbm_bytes = pairs * (L - c) * 2 * N_NEEDED * sz + pairs * nsp * (N_NEEDED if large else N_FWD) * sz * 2
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     line = {
@@ -340,7 +408,7 @@ def main():
                     "roofline": {"bound": "fma", "achieved": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12,
                                  "peak": peak, "unit": "TFLOP/s",
                                  "frac": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12 / peak}},
-        "roofline": {"bound": "fma", "kernel": {"gfwd": "pasif_gfwd_*", "bwd": "pasif_bwd_*"}[dom],
+        "roofline": {"bound": "fma", "kernel": ({"gfwd": "large_forward_kernel", "bwd": "large_backward_kernel"} if large else {"gfwd": "pasif_gfwd_*", "bwd": "pasif_bwd_*"})[dom],
                      "achieved": per_kernel[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": per_kernel[dom]["tflops"] / peak if per_kernel[dom]["tflops"] else None, "traffic": None,
                      "peak_source": "pasif_fma_peak register-resident FMA microbenchmark, same run (MEASURED_PEAKS.json has no FMA-pipe figure)",
