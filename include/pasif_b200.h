@@ -89,7 +89,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value);
 /* C++ source of the compile-time pattern traits of the currently loaded systems (used by tools/gen_aot_patterns.py
  * to pre-build kernels); writes at most cap bytes incl. NUL, *needed = bytes required */
 int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* needed);
-/* device FMA-pipe microbenchmark (register-resident dependent-free FMA chains): achieved TFLOP/s for the dtype */
+/* device pipe microbenchmarks (register-resident, no memory traffic): achieved TFLOP/s.  dtype PASIF_F64 / PASIF_F32: FMA pipe;
+ * 2: mma.sync m8n8k4 f64 (DMMA); 3: mma.sync m16n8k8 tf32 (fp32 accumulate) */
 int pasif_fma_peak(int device, int dtype, double* tflops);
 
 #ifdef __cplusplus

@@ -210,7 +210,7 @@ class Engine:
 
 def fma_peak(device=0, dtype="f64"):
     v = C.c_double()
-    if lib().pasif_fma_peak(int(device), {"f64": 0, "f32": 1}[dtype], C.byref(v)) != 0:
+    if lib().pasif_fma_peak(int(device), {"f64": 0, "f32": 1, "dmma": 2, "tf32_mma": 3}[dtype], C.byref(v)) != 0:
         raise PasifError(lib().pasif_last_error(None).decode())
     return v.value
 

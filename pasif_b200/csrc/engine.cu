@@ -182,6 +182,30 @@ __global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
 }
 
+// legacy tensor path peaks (mma.sync), 4 independent accumulator chains per warp
+__global__ void dmma_peak_kernel(double* out, int iters) {
+  double c[4][2] = {{0, 0}, {0, 0}, {0, 0}, {0, 0}};
+  const double a = 1.0 + threadIdx.x * 1e-9, b = 1.0 - threadIdx.x * 1e-9;
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                   : "+d"(c[k][0]), "+d"(c[k][1]) : "d"(a), "d"(b));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c[0][0] + c[1][1] + c[2][0] + c[3][1];
+}
+__global__ void tf32_mma_peak_kernel(float* out, int iters) {
+  float c[4][4] = {};
+  const unsigned a = __float_as_uint(1.0f), b = __float_as_uint(0.5f);
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int k = 0; k < 4; ++k)
+      asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                   : "+f"(c[k][0]), "+f"(c[k][1]), "+f"(c[k][2]), "+f"(c[k][3]) : "r"(a), "r"(a), "r"(a), "r"(a), "r"(b), "r"(b));
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = c[0][0] + c[1][1] + c[2][2] + c[3][3];
+}
+
 }  // namespace
 
 // ====================================================================================== NVRTC / driver entry points
@@ -1145,7 +1169,9 @@ int pasif_fma_peak(int device, int dtype, double* tflops) {
     for (int rep = 0; rep < 4; ++rep) {
       CUDA_CHECK(cudaEventRecord(a));
       if (dtype == PASIF_F32) fma_peak_kernel<float><<<blocks, threads>>>((float*)out, iters, 0.999f, 1e-3f);
-      else fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 0.999, 1e-3);
+      else if (dtype == PASIF_F64) fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 0.999, 1e-3);
+      else if (dtype == 2) dmma_peak_kernel<<<blocks, threads>>>((double*)out, iters / 8);
+      else tf32_mma_peak_kernel<<<blocks, threads>>>((float*)out, iters / 8);
       CUDA_CHECK(cudaEventRecord(b));
       CUDA_CHECK(cudaEventSynchronize(b));
       float ms = 0;
@@ -1154,7 +1180,9 @@ int pasif_fma_peak(int device, int dtype, double* tflops) {
     }
     CUDA_CHECK(cudaGetLastError());
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-    *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
+    if (dtype == 2) *tflops = 2.0 * 256.0 * 4.0 * (double)(iters / 8) * (threads / 32) * blocks / (best * 1e-3) / 1e12;        // m8n8k4
+    else if (dtype == 3) *tflops = 2.0 * 1024.0 * 4.0 * (double)(iters / 8) * (threads / 32) * blocks / (best * 1e-3) / 1e12;  // m16n8k8
+    else *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
   } catch (const std::exception& ex) {
     g_create_error = ex.what();
     return 2;

@@ -55,7 +55,8 @@ struct FwdArgs {
   int save_every, save_phase, save_layout, save_slots;
   int n_glob;
   const int* varmap;    // [N][n_inst] global state index of local variable i of instance j
-  // dense save (adjoint recompute): needed forward variables after EVERY step, [t - t0][NV][n_traj]
+  // dense save (adjoint recompute): needed forward variables after EVERY step, [t - t0][n_traj][NV]
+  // (one contiguous NV-vector per trajectory and step: a single 16-byte store / load when NV * sizeof(T) == 16)
   T* dense_ptr;
   // final state scattered to the user layout [e][n_glob] (getAmplitudes)
   T* final_user;
@@ -65,13 +66,51 @@ template <typename T>
 struct BwdArgs {
   const T* coef;        // [NCA][n_inst]  adjoint coefficient table
   T* lam;               // [NA][n_traj]   adjoint state, in/out
-  const T* dense;       // [i][NV][n_traj] forward state after step (t0 + i), i in [0, len)
+  const T* dense;       // [i][n_traj][NV] forward state after step (t0 + i), i in [0, len)
   const T* prev;        // [NF][n_traj]   forward state standing in for index i = -1 (a checkpoint slot)
   int len;              // number of backward steps
   int alias_local;      // literal-reference mode: local index of the aliased scratch slot (quirk A3) or -1000000
   int n_inst, E, n_traj;
   T h, h2, h6;
 };
+
+// ------------------------------------------------------------------------------------------------ NV-vector access
+template <typename T, int NV>
+PASIF_DEV void store_vec(T* dst, const T (&v)[NV > 0 ? NV : 1]) {
+  if constexpr (NV > 0 && (NV * sizeof(T)) % 16 == 0) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int k = 0; k < NV / 4; ++k) reinterpret_cast<float4*>(dst)[k] = make_float4(v[4 * k], v[4 * k + 1], v[4 * k + 2], v[4 * k + 3]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV / 2; ++k) reinterpret_cast<double2*>(dst)[k] = make_double2(v[2 * k], v[2 * k + 1]);
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) dst[k] = v[k];
+  }
+}
+template <typename T, int NV>
+PASIF_DEV void load_vec(const T* src, T (&v)[NV > 0 ? NV : 1]) {
+  if constexpr (NV > 0 && (NV * sizeof(T)) % 16 == 0) {
+    if constexpr (sizeof(T) == 4) {
+#pragma unroll
+      for (int k = 0; k < NV / 4; ++k) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(src) + k);
+        v[4 * k] = t.x; v[4 * k + 1] = t.y; v[4 * k + 2] = t.z; v[4 * k + 3] = t.w;
+      }
+    } else {
+#pragma unroll
+      for (int k = 0; k < NV / 2; ++k) {
+        const double2 t = __ldg(reinterpret_cast<const double2*>(src) + k);
+        v[2 * k] = t.x; v[2 * k + 1] = t.y;
+      }
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldg(src + k);
+  }
+}
 
 // ------------------------------------------------------------------------------------------------ derivative
 // y = K x + Gamma:(x,p) + Lambda:(x,p,p) + Psi:(x,p,p,p) + F fe        (forward: p == x)
@@ -145,72 +184,70 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
     save_slot = (u + a.save_every - 1) / a.save_every;          // first slot index with slot*every >= u
     save_cnt = save_slot * a.save_every - u;                    // steps (beyond t0) until that save fires
   }
-  T* dense = a.dense_ptr ? a.dense_ptr + p : nullptr;
+  constexpr int NVD = DV::NV > 0 ? DV::NV : 1;
+  T* dense = a.dense_ptr ? a.dense_ptr + (long long)p * DV::NV : nullptr;
+  const long long dense_stride = (long long)a.n_traj * DV::NV;
+
+  // everything that follows one RK4 step: dense save of the needed variables, periodic checkpoint / trajectory save
+  auto after_step = [&]() {
+    if (DV::NV > 0 && dense) {
+      T dv[NVD];
+#pragma unroll
+      for (int v = 0; v < DV::NV; ++v) dv[v] = q[DV::nv(v)];
+      store_vec<T, DV::NV>(dense, dv);
+      dense += dense_stride;
+    }
+    if (save_cnt == 0) {
+      if (save_slot < a.save_slots) {
+        if (a.save_layout == 0) {
+          T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
+#pragma unroll
+          for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
+        } else {
+          T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
+#pragma unroll
+          for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+        }
+      }
+      ++save_slot;
+      save_cnt = a.save_every;
+    }
+    --save_cnt;
+  };
 
   if (!a.half_mode) {
-    // register ring of gated excitation samples: e0 = e[t], e1 = e[t+1], ... prefetch distance 4 steps
+    // gated excitation samples e[t .. t+4] in registers; the time loop is unrolled by 4 so that the next four samples
+    // are requested a whole block (4 steps) before their first use and no register shuffling is left per step
     const T* ex = a.exc + (long long)a.t0 * E + e;
-    T e0 = ex[0], e1 = ex[E], e2 = ex[2 * E], e3 = ex[3 * E];
-    ex += 4 * E;
-    for (int t = a.t0; t < a.t1; ++t) {
-      const T e4 = *ex;                                          // e[t+4] (buffer is zero-padded past t1)
+    T e0 = ex[0], e1 = ex[E], e2 = ex[2 * E], e3 = ex[3 * E], e4 = ex[4 * E];   // buffer is zero-padded past t1
+    ex += 5 * E;
+    int t = a.t0;
+    for (; t + 4 <= a.t1; t += 4) {
+      const T n0 = ex[0], n1 = ex[E], n2 = ex[2 * E], n3 = ex[3 * E];           // e[t+5 .. t+8]
+      ex += 4 * E;
+      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, e1, e1, e2, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, e2, e2, e3, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, e3, e3, e4, h, h2, h6); after_step();
+      e0 = e4; e1 = n0; e2 = n1; e3 = n2; e4 = n3;
+    }
+    for (; t < a.t1; ++t) {
+      const T n0 = *ex;
       ex += E;
-      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6);
-      e0 = e1; e1 = e2; e2 = e3; e3 = e4;
-      if (DV::NV > 0 && dense) {
-#pragma unroll
-        for (int v = 0; v < DV::NV; ++v) dense[(long long)v * a.n_traj] = q[DV::nv(v)];
-        dense += (long long)DV::NV * a.n_traj;
-      }
-      if (save_cnt == 0) {
-        if (save_slot < a.save_slots) {
-          if (a.save_layout == 0) {
-            T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
-#pragma unroll
-            for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
-          } else {
-            T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
-#pragma unroll
-            for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
-          }
-        }
-        ++save_slot;
-        save_cnt = a.save_every;
-      }
-      --save_cnt;
+      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6); after_step();
+      e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = n0;
     }
   } else {
     // half-step mode (interpolation table): f[2t], f[2t+1], f[2t+2] -- preprocessed on the device by
-    // interp_force_kernel; two new samples per step
+    // prep_exc_half_kernel; two new samples per step, requested one step ahead
     const T* ex = a.exc + (long long)(2 * a.t0) * E + e;
-    T f0 = ex[0];
-    ex += E;
+    T f0 = ex[0], f1 = ex[E], f2 = ex[2 * E];
+    ex += 3 * E;
     for (int t = a.t0; t < a.t1; ++t) {
-      const T f1 = ex[0], f2 = ex[E];
+      const T g1 = ex[0], g2 = ex[E];                                            // f[2t+3], f[2t+4]
       ex += 2 * E;
-      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6);
-      f0 = f2;
-      if (DV::NV > 0 && dense) {
-#pragma unroll
-        for (int v = 0; v < DV::NV; ++v) dense[(long long)v * a.n_traj] = q[DV::nv(v)];
-        dense += (long long)DV::NV * a.n_traj;
-      }
-      if (save_cnt == 0) {
-        if (save_slot < a.save_slots) {
-          if (a.save_layout == 0) {
-            T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
-#pragma unroll
-            for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
-          } else {
-            T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
-#pragma unroll
-            for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
-          }
-        }
-        ++save_slot;
-        save_cnt = a.save_every;
-      }
-      --save_cnt;
+      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6); after_step();
+      f0 = f2; f1 = g1; f2 = g2;
     }
   }
 
@@ -247,15 +284,12 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
 
   const T h = a.h, h2 = a.h2, h6 = a.h6;
   const long long stride = (long long)PA::NV * a.n_traj;
-  const T* d = a.dense + p + (long long)(a.len - 1) * stride;    // state index i = len-1
+  const T* d = a.dense + (long long)p * PA::NV + (long long)(a.len - 1) * stride;    // state index i = len-1
   T qa[NV], qn[NV], qh[NV];
-#pragma unroll
-  for (int v = 0; v < PA::NV; ++v) qa[v] = d[(long long)v * a.n_traj];
+  load_vec<T, PA::NV>(d, qa);
   // software prefetch: qn = state i-1 of the CURRENT iteration, loaded one iteration ahead
-  if (a.len >= 2) {
-#pragma unroll
-    for (int v = 0; v < PA::NV; ++v) qn[v] = d[(long long)v * a.n_traj - stride];
-  } else {
+  if (a.len >= 2) load_vec<T, PA::NV>(d - stride, qn);
+  else {
 #pragma unroll
     for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
   }
@@ -268,11 +302,8 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
 #pragma unroll
     for (int v = 0; v < PA::NV; ++v) qb[v] = aliased ? qa[v] : qn[v];
     // prefetch state i-2 for the next iteration
-    if (i >= 2) {
-      const T* dn = d - 2 * stride;
-#pragma unroll
-      for (int v = 0; v < PA::NV; ++v) qn[v] = dn[(long long)v * a.n_traj];
-    } else if (i == 1) {
+    if (i >= 2) load_vec<T, PA::NV>(d - 2 * stride, qn);
+    else if (i == 1) {
 #pragma unroll
       for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
     }
