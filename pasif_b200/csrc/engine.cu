@@ -27,6 +27,7 @@
 #include "pattern.hpp"
 #include "rk4_kernels.cuh"
 #include "large_kernels.cuh"
+#include "stage_kernels.cuh"
 
 using namespace pasif_host;
 
@@ -365,7 +366,8 @@ struct pasif_engine {
   std::string err;
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the tile kernels
-  long long large_classes = 0, large_gemm_classes = 0;
+  long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
+  bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
   int block = PASIF_BLOCK, n_sm = 148;
   double last_ms = 0;
   long long last_launches = 0, jit_compiles = 0, aot_hits = 0, jit_cache_hits = 0;
@@ -726,6 +728,7 @@ Schedule reference_schedule(uint32_t n) {       // reference src/__GpuDriver.cu:
 }
 
 #include "large_host.inc"
+#include "stage_host.inc"
 void LargeClassDeleter::operator()(LargeClass* p) const {
   if (p) { p->release(); delete p; }
 }
@@ -1050,7 +1053,9 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     if (b < 32 || b > PASIF_BLOCK || (b & 31)) throw std::runtime_error("block must be a multiple of 32 in [32, " + std::to_string(PASIF_BLOCK) + "]");
     e->block = b;
   } else if (k == "gemm") {
-    e->gemm_on = (v == "on" || v == "1");
+    // "on" / "stage": per-stage batched GEMM (stage_kernels.cuh); "tile": GEMM inside the tile kernels; "off": row programs
+    e->gemm_on = (v == "on" || v == "1" || v == "stage" || v == "tile");
+    e->gemm_stage = (v != "tile");
   } else if (k == "large_threshold") {
     e->large_threshold = std::atoi(v.c_str());
   } else if (k == "overlap") {
@@ -1125,6 +1130,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "dtype") *value = e->dtype;
   else if (k == "large_classes") *value = (double)e->large_classes;
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
+  else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
+  else if (k == "gemm_launches") *value = (double)e->gemm_launches;
   else if (k == "aot_table_size") *value = (double)aot_table().size();
   else if (k == "ms_fwd") *value = e->kind_ms[0];
   else if (k == "ms_gfwd") *value = e->kind_ms[1];

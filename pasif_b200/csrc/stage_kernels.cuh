@@ -1,0 +1,370 @@
+// stage_kernels.cuh -- dense-operator path: one RK4 STAGE of the whole batch = one batched GEMM + one fused update.
+//
+// When a large component has a DENSE linear operator K' shared by every trajectory (BASELINE config 4, "many systems
+// share a dense B"), K'.X is 2 N^2 flops per trajectory-stage against O(N) for everything else.  Keeping the state of
+// a tile on chip (large_kernels.cuh) then re-streams K' from L2 for every 8-16 trajectories (~2 flop/byte); instead
+// the state lives in HBM, trajectory-major [p][NR] (K-contiguous for both GEMM operands), and every stage is
+//     Y[p][m]  = sum_k Kd[m][k] * X[p][k]                 a real GEMM  [NR x NR] . [NR x P]   (tensor cores)
+//     update   : y = Y + Gamma/Lambda/Psi row terms + F e ; S, next stage vector, Q             (HBM-bound, fused)
+// N/8 (fp64) .. N/4 (fp32) flop per state byte, so the HBM round trip of the state costs ~10 % of the GEMM at N = 512.
+// This is the reference's own per-stage structure (cusparseSpMM over the [N x E] operand, src/__GpuDriver.cu:795-807)
+// with the SpMM replaced by a tensor-core GEMM and its ~16 element-wise / atomic micro-kernels by ONE update kernel.
+//
+//   fp64: dgemm_tn_dmma_kernel    mma.sync.m8n8k4.f64 (DMMA), cp.async 3-stage shared-memory pipeline
+//   fp32: sgemm_tn_3xtf32_kernel  3xTF32 split (hi*hi + lo*hi + hi*lo, fp32 accumulate) -- see stage_tcgen05.cuh for
+//         the tcgen05/TMEM/TMA version used on sm_100a
+#pragma once
+
+#include "large_kernels.cuh"
+
+namespace pasif_stage {
+
+using pasif_large::Tables;
+
+// ------------------------------------------------------------------------------------------------ fused stage update
+template <typename T>
+struct UpdArgs {
+  Tables tb;             // row programs without K (WK = 0); NPR = row stride of the set-point arrays
+  const T* vals;         // [n_inst][coef_stride]
+  const T* Y;            // [P][NR] GEMM result K'.X
+  const T* X;            // [P][NR] stage vector the derivative is evaluated at
+  const T* Pa;           // [P][NPR] set-point vector (forward: == X)
+  const T* Pb;           // adjoint half stage: P = (Pa + Pb) / 2 ; else nullptr
+  T* Q;                  // [P][NR] state
+  T* S;                  // [P][NR] running stage sum
+  T* Xn;                 // [P][NR] next stage vector (stage 4: the new state)
+  T* Xn_hi;              // fp32 only: tf32 split of Xn for the next 3xTF32 GEMM
+  T* Xn_lo;
+  const T* fe;           // excitation samples of this stage [E] (nullptr: unforced)
+  int stage;             // 1..4
+  int E, n_traj;
+  T h, h2, h6;
+};
+
+template <typename T, int U>
+__global__ void __launch_bounds__(1024) stage_update_kernel(const UpdArgs<T> a) {
+  const Tables& tb = a.tb;
+  const int NR = tb.NR, NPR = tb.NPR;
+  const int r = threadIdx.x;
+  const long long p0 = (long long)blockIdx.x * U;
+  if (p0 >= a.n_traj) return;
+  const int4 w = __ldg(tb.widths + (r >> 5));
+  const T* X = a.X + p0 * NR;
+  const T* Pa = a.Pa + p0 * NPR;
+  const T* Pb = a.Pb ? a.Pb + p0 * NPR : nullptr;
+  T y[U];
+  int inst[U];
+#pragma unroll
+  for (int b = 0; b < U; ++b) {
+    const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;      // clamp: lanes past the batch recompute the last one
+    inst[b] = (int)(p / a.E);
+    y[b] = a.Y[(p0 + b) * NR + r];                                      // arrays are padded to a multiple of U rows
+  }
+  auto P = [&](int b, int c) -> T {
+    const T v = Pa[(long long)b * NPR + c];
+    return Pb ? T(.5) * (v + Pb[(long long)b * NPR + c]) : v;
+  };
+  const size_t cs = (size_t)tb.coef_stride;
+  const T* v0 = a.vals + r;
+  size_t off = (size_t)tb.WK * NR;
+  for (int j = 0; j < w.y; ++j) {
+    const int2 ix = __ldg(tb.g_idx + j * NR + r);
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      const T gv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
+      y[b] = fma(gv * X[(long long)b * NR + ix.x], P(b, ix.y), y[b]);
+    }
+  }
+  off += (size_t)tb.WG * NR;
+  for (int j = 0; j < w.z; ++j) {
+    const int4 ix = __ldg(tb.l_idx + j * NR + r);
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      const T lv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
+      y[b] = fma(lv * X[(long long)b * NR + ix.x] * P(b, ix.y), P(b, ix.z), y[b]);
+    }
+  }
+  off += (size_t)tb.WL * NR;
+  for (int j = 0; j < w.w; ++j) {
+    const int4 ix = __ldg(tb.p_idx + j * NR + r);
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      const T pv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
+      y[b] = fma(pv * X[(long long)b * NR + ix.x] * P(b, ix.y) * P(b, ix.z), P(b, ix.w), y[b]);
+    }
+  }
+  off += (size_t)tb.WP * NR;
+  if (a.fe) {
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;
+      const T fr = __ldg(v0 + inst[b] * cs + off);
+      y[b] = fma(fr, __ldg(a.fe + (int)(p - (long long)inst[b] * a.E)), y[b]);
+    }
+  }
+#pragma unroll
+  for (int b = 0; b < U; ++b) {
+    const long long o = (p0 + b) * NR + r;
+    const T q = a.Q[o];
+    T xn;
+    if (a.stage == 1) { a.S[o] = y[b]; xn = fma(a.h2, y[b], q); }
+    else if (a.stage == 2) { a.S[o] = fma(T(2), y[b], a.S[o]); xn = fma(a.h2, y[b], q); }
+    else if (a.stage == 3) { a.S[o] = fma(T(2), y[b], a.S[o]); xn = fma(a.h, y[b], q); }
+    else { xn = fma(a.h6, a.S[o] + y[b], q); a.Q[o] = xn; }
+    a.Xn[o] = xn;
+    if constexpr (sizeof(T) == 4) {
+      if (a.Xn_hi) {
+        const float hi = __uint_as_float(pasif_large::f2tf32(xn));
+        a.Xn_hi[o] = hi;
+        a.Xn_lo[o] = __uint_as_float(pasif_large::f2tf32(xn - hi));
+      }
+    }
+  }
+}
+
+// state initialisation: Q = X = ic (per instance), optional tf32 split
+template <typename T>
+__global__ void stage_init_kernel(const T* __restrict__ ic, T* Q, T* X, T* X_hi, T* X_lo, int NR, int E, long long n_traj,
+                                  long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const long long p = idx / NR;
+  const int r = (int)(idx - p * NR);
+  const T v = p < n_traj ? ic[(p / E) * NR + r] : T(0);
+  if (Q) Q[idx] = v;
+  X[idx] = v;
+  if constexpr (sizeof(T) == 4) {
+    if (X_hi) {
+      const float hi = __uint_as_float(pasif_large::f2tf32(v));
+      X_hi[idx] = hi;
+      X_lo[idx] = __uint_as_float(pasif_large::f2tf32(v - hi));
+    }
+  }
+}
+
+// copy a state array into the stage-vector buffers (start of a recompute chunk): X = src (+ split)
+template <typename T>
+__global__ void stage_load_kernel(const T* __restrict__ src, T* Q, T* X, T* X_hi, T* X_lo, long long total) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= total) return;
+  const T v = src[idx];
+  if (Q) Q[idx] = v;
+  X[idx] = v;
+  if constexpr (sizeof(T) == 4) {
+    if (X_hi) {
+      const float hi = __uint_as_float(pasif_large::f2tf32(v));
+      X_hi[idx] = hi;
+      X_lo[idx] = __uint_as_float(pasif_large::f2tf32(v - hi));
+    }
+  }
+}
+
+// [p][NR] state -> user layout [slot][E][n_glob] through varmap [n_inst][NR]
+template <typename T>
+__global__ void stage_scatter_kernel(const T* __restrict__ Q, const int* __restrict__ varmap, T* __restrict__ out, int NR, int E,
+                                     int n_glob, long long n_traj) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n_traj * NR) return;
+  const long long p = idx / NR;
+  const int r = (int)(idx - p * NR);
+  const long long inst = p / E;
+  const int g = varmap[inst * NR + r];
+  if (g >= 0) out[(p - inst * E) * n_glob + g] = Q[idx];
+}
+
+// ------------------------------------------------------------------------------------------------ fp64 GEMM (DMMA)
+// Y[p][m] = sum_k A[m][k] * B[p][k];  A = Kd [Mpad][K] row-major, B = X [Ppad][K] row-major (both K-contiguous),
+// Mpad % 64 == 0, Ppad % 128 == 0, K % 16 == 0.  CTA tile 64 (m) x 128 (p), 8 warps as 2 x 4, warp tile 32 x 32,
+// 3-stage cp.async pipeline; shared-memory rows padded to 20 doubles so that every DMMA fragment load (8 rows x 4
+// consecutive doubles per half-warp) is bank-conflict free.
+constexpr int DG_BM = 64, DG_BN = 128, DG_BK = 16, DG_LD = 20, DG_STAGES = 3;
+constexpr int DG_SMEM = DG_STAGES * (DG_BM + DG_BN) * DG_LD * 8;
+
+__device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
+
+__global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B,
+                                                            double* __restrict__ Y, int M, int K, int ldy) {
+  extern __shared__ __align__(16) unsigned char dg_smem[];
+  double* sA = reinterpret_cast<double*>(dg_smem);                    // [STAGES][BM][LD]
+  double* sB = sA + DG_STAGES * DG_BM * DG_LD;                        // [STAGES][BN][LD]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;
+  const int m0 = blockIdx.x * DG_BM;
+  const long long p0 = (long long)blockIdx.y * DG_BN;
+  const double* Ag = A + (size_t)m0 * K;
+  const double* Bg = B + (size_t)p0 * K;
+  const int nkb = K / DG_BK;
+
+  auto issue = [&](int kb, int st) {
+    // A tile: 64 rows x 16 doubles = 512 16-byte chunks; B tile: 128 rows -> 1024 chunks
+    double* a = sA + st * DG_BM * DG_LD;
+    double* b = sB + st * DG_BN * DG_LD;
+#pragma unroll
+    for (int c = tid; c < DG_BM * 8; c += 256) {
+      const int row = c >> 3, ch = c & 7;
+      cp_async16(a + row * DG_LD + ch * 2, Ag + (size_t)row * K + kb * DG_BK + ch * 2);
+    }
+#pragma unroll
+    for (int c = tid; c < DG_BN * 8; c += 256) {
+      const int row = c >> 3, ch = c & 7;
+      cp_async16(b + row * DG_LD + ch * 2, Bg + (size_t)row * K + kb * DG_BK + ch * 2);
+    }
+  };
+
+  double acc[4][4][2];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+
+  for (int s = 0; s < DG_STAGES - 1; ++s) {
+    if (s < nkb) issue(s, s);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    cp_async_wait<DG_STAGES - 2>();
+    __syncthreads();
+    if (kb + DG_STAGES - 1 < nkb) issue(kb + DG_STAGES - 1, (kb + DG_STAGES - 1) % DG_STAGES);
+    cp_async_commit();
+    const double* a = sA + (kb % DG_STAGES) * DG_BM * DG_LD + (wm * 32 + g) * DG_LD + t;
+    const double* b = sB + (kb % DG_STAGES) * DG_BN * DG_LD + (wn * 32 + g) * DG_LD + t;
+#pragma unroll
+    for (int kk = 0; kk < DG_BK; kk += 4) {
+      double af[4], bf[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) af[i] = a[i * 8 * DG_LD + kk];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) bf[j] = b[j * 8 * DG_LD + kk];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                       : "+d"(acc[i][j][0]), "+d"(acc[i][j][1])
+                       : "d"(af[i]), "d"(bf[j]));
+    }
+  }
+  cp_async_wait<0>();
+  // C fragment: row m = g, columns p = 2t, 2t+1
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + wm * 32 + i * 8 + g;
+    if (m >= M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long p = p0 + wn * 32 + j * 8 + 2 * t;
+      Y[p * ldy + m] = acc[i][j][0];
+      Y[(p + 1) * ldy + m] = acc[i][j][1];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ fp32 GEMM (3xTF32, mma.sync)
+// Same tiling idea with m16n8k8 tf32: CTA tile 64 (m) x 128 (p), BK = 16 floats, operands pre-split into hi / lo
+// (both exactly representable in tf32).  Kept as the portable reference for the tcgen05 kernel in stage_tcgen05.cuh.
+constexpr int SG_BM = 64, SG_BN = 128, SG_BK = 16, SG_LD = 20, SG_STAGES = 3;
+constexpr int SG_SMEM = SG_STAGES * 2 * (SG_BM + SG_BN) * SG_LD * 4;
+
+__global__ void __launch_bounds__(256) sgemm_tn_3xtf32_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
+                                                              const float* __restrict__ Bhi, const float* __restrict__ Blo,
+                                                              float* __restrict__ Y, int M, int K, int ldy) {
+  extern __shared__ __align__(16) unsigned char dg_smem[];
+  float* sAh = reinterpret_cast<float*>(dg_smem);                     // [STAGES][BM][LD]
+  float* sAl = sAh + SG_STAGES * SG_BM * SG_LD;
+  float* sBh = sAl + SG_STAGES * SG_BM * SG_LD;                       // [STAGES][BN][LD]
+  float* sBl = sBh + SG_STAGES * SG_BN * SG_LD;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 2, wn = warp & 3;                            // warp tile 32 (m) x 32 (p)
+  const int m0 = blockIdx.x * SG_BM;
+  const long long p0 = (long long)blockIdx.y * SG_BN;
+  const int nkb = K / SG_BK;
+
+  auto issue = [&](int kb, int st) {
+    // rows of 16 floats = 4 chunks of 16 bytes
+    for (int c = tid; c < SG_BM * 4; c += 256) {
+      const int row = c >> 2, ch = c & 3;
+      const size_t go = (size_t)(m0 + row) * K + kb * SG_BK + ch * 4;
+      cp_async16(sAh + (st * SG_BM + row) * SG_LD + ch * 4, Ahi + go);
+      cp_async16(sAl + (st * SG_BM + row) * SG_LD + ch * 4, Alo + go);
+    }
+    for (int c = tid; c < SG_BN * 4; c += 256) {
+      const int row = c >> 2, ch = c & 3;
+      const size_t go = (size_t)(p0 + row) * K + kb * SG_BK + ch * 4;
+      cp_async16(sBh + (st * SG_BN + row) * SG_LD + ch * 4, Bhi + go);
+      cp_async16(sBl + (st * SG_BN + row) * SG_LD + ch * 4, Blo + go);
+    }
+  };
+
+  float acc[2][4][4];
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) acc[i][j][c] = 0.f;
+
+  for (int s = 0; s < SG_STAGES - 1; ++s) {
+    if (s < nkb) issue(s, s);
+    cp_async_commit();
+  }
+  for (int kb = 0; kb < nkb; ++kb) {
+    cp_async_wait<SG_STAGES - 2>();
+    __syncthreads();
+    if (kb + SG_STAGES - 1 < nkb) issue(kb + SG_STAGES - 1, (kb + SG_STAGES - 1) % SG_STAGES);
+    cp_async_commit();
+    const int st = kb % SG_STAGES;
+    const int ao = (st * SG_BM + wm * 32 + g) * SG_LD + t;
+    const int bo = (st * SG_BN + wn * 32 + g) * SG_LD + t;
+#pragma unroll
+    for (int kk = 0; kk < SG_BK; kk += 8) {
+      unsigned ah[2][4], al[2][4], bh[4][2], bl[4][2];
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int o = ao + i * 16 * SG_LD + kk;
+        ah[i][0] = __float_as_uint(sAh[o]);               al[i][0] = __float_as_uint(sAl[o]);
+        ah[i][1] = __float_as_uint(sAh[o + 8 * SG_LD]);   al[i][1] = __float_as_uint(sAl[o + 8 * SG_LD]);
+        ah[i][2] = __float_as_uint(sAh[o + 4]);           al[i][2] = __float_as_uint(sAl[o + 4]);
+        ah[i][3] = __float_as_uint(sAh[o + 8 * SG_LD + 4]); al[i][3] = __float_as_uint(sAl[o + 8 * SG_LD + 4]);
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int o = bo + j * 8 * SG_LD + kk;
+        bh[j][0] = __float_as_uint(sBh[o]);     bl[j][0] = __float_as_uint(sBl[o]);
+        bh[j][1] = __float_as_uint(sBh[o + 4]); bl[j][1] = __float_as_uint(sBl[o + 4]);
+      }
+#pragma unroll
+      for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+#define PS_MMA(A_, B_)                                                                                                   \
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};" \
+               : "+f"(acc[i][j][0]), "+f"(acc[i][j][1]), "+f"(acc[i][j][2]), "+f"(acc[i][j][3])                           \
+               : "r"(A_[i][0]), "r"(A_[i][1]), "r"(A_[i][2]), "r"(A_[i][3]), "r"(B_[j][0]), "r"(B_[j][1]))
+          PS_MMA(al, bh);
+          PS_MMA(ah, bl);
+          PS_MMA(ah, bh);
+#undef PS_MMA
+        }
+    }
+  }
+  cp_async_wait<0>();
+#pragma unroll
+  for (int i = 0; i < 2; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const long long p = p0 + wn * 32 + j * 8 + 2 * t;
+      const int m = m0 + wm * 32 + i * 16 + g;
+      if (m < M) { Y[p * ldy + m] = acc[i][j][0]; Y[(p + 1) * ldy + m] = acc[i][j][1]; }
+      if (m + 8 < M) { Y[p * ldy + m + 8] = acc[i][j][2]; Y[(p + 1) * ldy + m + 8] = acc[i][j][3]; }
+    }
+}
+
+}  // namespace pasif_stage

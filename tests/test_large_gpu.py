@@ -60,12 +60,17 @@ def chain_case(ndof, dense, E, L, n_sys=1, seed=3):
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 @pytest.mark.parametrize("compat", ["reference", "clean"])
-@pytest.mark.parametrize("dense", [False, True])
-def test_chain_matches_oracle(dense, compat, prec):
+@pytest.mark.parametrize("mode", ["sparse", "dense-stage", "dense-tile"])
+def test_chain_matches_oracle(mode, compat, prec):
+    """sparse: row programs in the tile kernels; dense-stage: per-stage batched GEMM + fused update with the state in
+    HBM (the default for a dense shared K'); dense-tile: GEMM inside the tile kernels."""
+    dense = mode != "sparse"
     case = chain_case(40, dense, E=11, L=700)
-    a = run_case(capi.engine_class(prec, compat), case)
+    a = run_case(capi.engine_class(prec, compat), case, options={"gemm": "tile"} if mode == "dense-tile" else None)
     b = run_case(_oracle(prec, compat), case)
     assert a["_p"]._query("large_classes") >= 1
+    assert (a["_p"]._query("large_stage_classes") >= 1) == (mode == "dense-stage")
+    assert (a["_p"]._query("large_gemm_classes") >= 1) == dense
     n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
     assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
     assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
@@ -75,12 +80,15 @@ def test_chain_matches_oracle(dense, compat, prec):
 def test_gemm_path_is_used_and_agrees_with_row_programs():
     """Dense shared K': the tensor-core path (DMMA) and the sparse row programs (gemm=off) give the same fp64 result."""
     case = chain_case(48, True, E=16, L=400)
-    a = run_case(capi.engine_class("f64"), case)
     b = run_case(capi.engine_class("f64"), case, options={"gemm": "off"})
-    assert a["_p"]._query("large_gemm_classes") >= 1 and b["_p"]._query("large_gemm_classes") == 0
+    assert b["_p"]._query("large_gemm_classes") == 0
     n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
-    assert col_err(a["amplitudes"], b["amplitudes"], n) < 1e-12
-    assert col_err(a["gradient"], b["gradient"], na) < 1e-12
+    for mode in ("stage", "tile"):
+        a = run_case(capi.engine_class("f64"), case, options={"gemm": mode})
+        assert a["_p"]._query("large_gemm_classes") >= 1
+        assert col_err(a["amplitudes"], b["amplitudes"], n) < 1e-12
+        assert rel_err(a["trajectory"], b["trajectory"]) < 1e-12
+        assert col_err(a["gradient"], b["gradient"], na) < 1e-12
 
 
 @pytest.mark.parametrize("prec", ["f64", "f32"])
