@@ -92,6 +92,10 @@ int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* need
 /* device pipe microbenchmarks (register-resident, no memory traffic): achieved TFLOP/s.  dtype PASIF_F64 / PASIF_F32: FMA pipe;
  * 2: mma.sync m8n8k4 f64 (DMMA); 3: mma.sync m16n8k8 tf32 (fp32 accumulate) */
 int pasif_fma_peak(int device, int dtype, double* tflops);
+/* isolated check of the dense-operator path's GEMM kernels (no reference counterpart: replaces the cusparseSpMM of
+ * src/__GpuDriver.cu:795-807 for a dense shared K'): y[p][m] = sum_k kd[m][k] * x[p][k], kd [n][n], x / y [n_traj][n], row-major doubles.
+ * mode 0: mma.sync kernel of the dtype (fp64 DMMA, fp32 3xTF32); mode 1: tcgen05 3xTF32 (fp32 only) */
+int pasif_debug_gemm(int device, int dtype, int mode, uint32_t n, uint64_t n_traj, const double* kd, const double* x, double* y);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ pasif_set_fwd_k pasif_set_fwd_gamma pasif_set_fwd_lambda pasif_set_fwd_psi pasif
 pasif_set_bwd_k pasif_set_bwd_gamma pasif_set_bwd_lambda pasif_set_bwd_psi pasif_set_bwd_force pasif_set_bwd_ic pasif_alloc_adjoint
 pasif_set_interp pasif_set_modulation pasif_set_option
 pasif_get_amplitudes pasif_trajectory_size pasif_get_trajectory pasif_get_gradient pasif_get_gradient_reduced
-pasif_get_gradient_reduced_device pasif_query pasif_emit_patterns pasif_fma_peak""".split()
+pasif_get_gradient_reduced_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm""".split()
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -60,6 +60,7 @@ def lib():
         L.pasif_query.argtypes = [C.c_void_p, C.c_char_p, _dp]
         L.pasif_emit_patterns.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.pasif_fma_peak.argtypes = [C.c_int, C.c_int, _dp]
+        L.pasif_debug_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64, _dp, _dp, _dp]
         _lib = L
     return _lib
 
@@ -213,6 +214,18 @@ def fma_peak(device=0, dtype="f64"):
     if lib().pasif_fma_peak(int(device), {"f64": 0, "f32": 1, "dmma": 2, "tf32_mma": 3}[dtype], C.byref(v)) != 0:
         raise PasifError(lib().pasif_last_error(None).decode())
     return v.value
+
+
+def debug_gemm(kd, x, dtype="f32", mode=0, device=0):
+    """y[p][m] = sum_k kd[m][k] x[p][k] through one of the dense-operator path's GEMM kernels (see pasif_debug_gemm)."""
+    kd, pk = _d(kd)
+    x, px = _d(x)
+    n, P = kd.shape[0], x.shape[0]
+    assert kd.shape == (n, n) and x.shape == (P, n)
+    y = np.empty((P, n), dtype=np.float64)
+    if lib().pasif_debug_gemm(int(device), {"f64": 0, "f32": 1}[dtype], int(mode), n, P, pk, px, y.ctypes.data_as(_dp)) != 0:
+        raise PasifError(lib().pasif_last_error(None).decode())
+    return y
 
 
 def host_engine_class(dtype="f64"):

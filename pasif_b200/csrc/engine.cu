@@ -28,6 +28,7 @@
 #include "rk4_kernels.cuh"
 #include "large_kernels.cuh"
 #include "stage_kernels.cuh"
+#include "stage_tcgen05.cuh"
 
 using namespace pasif_host;
 
@@ -367,6 +368,7 @@ struct pasif_engine {
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the tile kernels
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
+  bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
   bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
   int block = PASIF_BLOCK, n_sm = 148;
   double last_ms = 0;
@@ -1056,6 +1058,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     // "on" / "stage": per-stage batched GEMM (stage_kernels.cuh); "tile": GEMM inside the tile kernels; "off": row programs
     e->gemm_on = (v == "on" || v == "1" || v == "stage" || v == "tile");
     e->gemm_stage = (v != "tile");
+  } else if (k == "tcgen05") {
+    e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "large_threshold") {
     e->large_threshold = std::atoi(v.c_str());
   } else if (k == "overlap") {
@@ -1158,6 +1162,18 @@ int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* need
     buf[n] = 0;
   }
   PASIF_CATCH(e)
+}
+
+int pasif_debug_gemm(int device, int dtype, int mode, uint32_t n, uint64_t n_traj, const double* kd, const double* x, double* y) {
+  try {
+    CUDA_CHECK(cudaSetDevice(device));
+    if (dtype == PASIF_F32) debug_gemm<float>(mode, (int)n, (long long)n_traj, kd, x, y);
+    else debug_gemm<double>(mode, (int)n, (long long)n_traj, kd, x, y);
+  } catch (const std::exception& ex) {
+    g_create_error = ex.what();
+    return 2;
+  }
+  return 0;
 }
 
 int pasif_fma_peak(int device, int dtype, double* tflops) {

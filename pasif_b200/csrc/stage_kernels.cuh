@@ -37,15 +37,19 @@ struct UpdArgs {
   T* Xn_lo;
   const T* fe;           // excitation samples of this stage [E] (nullptr: unforced)
   int stage;             // 1..4
-  int E, n_traj;
+  int E, n_traj;         // n_traj: trajectories of THIS launch (a contiguous part of the batch)
+  long long p_base;      // global index of the part's first trajectory (instance = (p_base + p) / E)
   T h, h2, h6;
 };
 
+// grid (ceil(n_traj / U), NR / UPD_ROWS): a CTA of UPD_ROWS threads = UPD_ROWS consecutive rows of U trajectories
+constexpr int UPD_ROWS = 32;
+
 template <typename T, int U>
-__global__ void __launch_bounds__(1024) stage_update_kernel(const UpdArgs<T> a) {
+__global__ void __launch_bounds__(UPD_ROWS, 16) stage_update_kernel(const UpdArgs<T> a) {
   const Tables& tb = a.tb;
   const int NR = tb.NR, NPR = tb.NPR;
-  const int r = threadIdx.x;
+  const int r = blockIdx.y * UPD_ROWS + threadIdx.x;
   const long long p0 = (long long)blockIdx.x * U;
   if (p0 >= a.n_traj) return;
   const int4 w = __ldg(tb.widths + (r >> 5));
@@ -57,7 +61,7 @@ __global__ void __launch_bounds__(1024) stage_update_kernel(const UpdArgs<T> a) 
 #pragma unroll
   for (int b = 0; b < U; ++b) {
     const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;      // clamp: lanes past the batch recompute the last one
-    inst[b] = (int)(p / a.E);
+    inst[b] = (int)((a.p_base + p) / a.E);
     y[b] = a.Y[(p0 + b) * NR + r];                                      // arrays are padded to a multiple of U rows
   }
   auto P = [&](int b, int c) -> T {
@@ -99,7 +103,7 @@ __global__ void __launch_bounds__(1024) stage_update_kernel(const UpdArgs<T> a) 
     for (int b = 0; b < U; ++b) {
       const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;
       const T fr = __ldg(v0 + inst[b] * cs + off);
-      y[b] = fma(fr, __ldg(a.fe + (int)(p - (long long)inst[b] * a.E)), y[b]);
+      y[b] = fma(fr, __ldg(a.fe + (int)(a.p_base + p - (long long)inst[b] * a.E)), y[b]);
     }
   }
 #pragma unroll
@@ -125,12 +129,12 @@ __global__ void __launch_bounds__(1024) stage_update_kernel(const UpdArgs<T> a) 
 // state initialisation: Q = X = ic (per instance), optional tf32 split
 template <typename T>
 __global__ void stage_init_kernel(const T* __restrict__ ic, T* Q, T* X, T* X_hi, T* X_lo, int NR, int E, long long n_traj,
-                                  long long total) {
+                                  long long total, long long p_base) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= total) return;
   const long long p = idx / NR;
   const int r = (int)(idx - p * NR);
-  const T v = p < n_traj ? ic[(p / E) * NR + r] : T(0);
+  const T v = p < n_traj ? ic[((p_base + p) / E) * NR + r] : T(0);
   if (Q) Q[idx] = v;
   X[idx] = v;
   if constexpr (sizeof(T) == 4) {
@@ -162,14 +166,14 @@ __global__ void stage_load_kernel(const T* __restrict__ src, T* Q, T* X, T* X_hi
 // [p][NR] state -> user layout [slot][E][n_glob] through varmap [n_inst][NR]
 template <typename T>
 __global__ void stage_scatter_kernel(const T* __restrict__ Q, const int* __restrict__ varmap, T* __restrict__ out, int NR, int E,
-                                     int n_glob, long long n_traj) {
+                                     int n_glob, long long n_traj, long long p_base) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= n_traj * NR) return;
   const long long p = idx / NR;
   const int r = (int)(idx - p * NR);
-  const long long inst = p / E;
+  const long long inst = (p_base + p) / E;
   const int g = varmap[inst * NR + r];
-  if (g >= 0) out[(p - inst * E) * n_glob + g] = Q[idx];
+  if (g >= 0) out[(p_base + p - inst * E) * n_glob + g] = Q[idx];
 }
 
 // ------------------------------------------------------------------------------------------------ fp64 GEMM (DMMA)

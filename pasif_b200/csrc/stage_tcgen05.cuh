@@ -1,0 +1,173 @@
+// stage_tcgen05.cuh -- fp32 stage GEMM of the dense-operator path on the 5th-generation tensor cores (sm_100a):
+//     Y[p][m] = sum_k Kd[m][k] * X[p][k]        3xTF32:  Xhi.Kdhi + Xlo.Kdhi + Xhi.Kdlo,  fp32 accumulate in TMEM
+// UMMA M = 128 trajectories (TMEM lanes), N = 192 rows of K' (TMEM columns), K-block = 32 floats = one 128-byte
+// swizzle atom.  Operands are K-major in shared memory, staged by TMA (cp.async.bulk.tensor.2d, SWIZZLE_128B) through
+// a 2-stage full/empty mbarrier ring; tcgen05.mma is issued by one elected thread; the accumulator is read back with
+// tcgen05.ld (32 lanes x 32 columns per warp and instruction) and written to Y as whole 128-byte lines per thread.
+//   warp 0 / lane 0 : TMA producer          warp 1 / lane 0 : MMA issuer          warps 0-3 : epilogue
+// Descriptor encodings follow the CUTLASS sm100 headers (cute/arch/mma_sm100_desc.hpp): shared-memory descriptor
+// {start>>4 [0,14), LBO>>4 [16,30), SBO>>4 [32,46), version=1 [46,48), layout SWIZZLE_128B=2 [61,64)}, instruction
+// descriptor {c_format F32=1 [4,6), a/b_format TF32=2 [7,10)/[10,13), a/b K-major, N>>3 [17,23), M>>4 [24,29)}.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace pasif_tc {
+
+constexpr int TC_BM = 128;          // trajectories per tile (UMMA M)
+constexpr int TC_BN = 192;          // rows of K' per tile   (UMMA N)
+constexpr int TC_BK = 32;           // floats per k-block (128 bytes)
+constexpr int TC_STAGES = 2;
+constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB (one of hi / lo)
+constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;          // 24 KB
+constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;
+constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+constexpr int TC_TMEM_COLS = 256;   // power of two >= TC_BN
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "WAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+      "@p bra WAIT_DONE;\n"
+      "bra WAIT_LOOP;\n"
+      "WAIT_DONE:\n"
+      "}\n" ::"r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(smem_u32(dst)),
+               "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  // K-major, SWIZZLE_128B: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart (SBO), LBO unused (1)
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// grid (m tiles, p tiles), 128 threads.  mapA*: X hi / lo [Ppad][K]; mapB*: Kd hi / lo [Mpad][K]; p_row0: first row of
+// this launch's part inside the X arrays; Y is already offset to the part.
+__global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAh,
+                                                                         const __grid_constant__ CUtensorMap mapAl,
+                                                                         const __grid_constant__ CUtensorMap mapBh,
+                                                                         const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y,
+                                                                         int M, int K, int ldy, int p_row0) {
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* done = empty + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = blockIdx.x * TC_BN;
+  const int p0 = blockIdx.y * TC_BM;
+  const int nkb = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapAl) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 0 && lane == 0) {
+    // ---- TMA producer
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&empty[s], ph ^ 1);                       // first pass: succeeds immediately (preceding phase)
+      unsigned char* st = base + s * TC_STAGE_BYTES;
+      mbar_expect_tx(&full[s], TC_STAGE_BYTES);
+      tma_load_2d(st, &mapAh, &full[s], kb * TC_BK, p_row0 + p0);
+      tma_load_2d(st + TC_A_BYTES, &mapAl, &full[s], kb * TC_BK, p_row0 + p0);
+      tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], kb * TC_BK, m0);
+      tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], kb * TC_BK, m0);
+    }
+  } else if (warp == 1 && lane == 0) {
+    // ---- MMA issuer
+    const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+      const uint32_t sa = smem_u32(base + s * TC_STAGE_BYTES);
+      const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+      for (int kk = 0; kk < TC_BK / 8; ++kk) {            // UMMA K = 8 tf32 = 32 bytes inside the swizzle atom
+        const uint32_t o = kk * 32;
+        umma_tf32(tmem_d, umma_desc_sw128(a_lo + o), umma_desc_sw128(b_hi + o), idesc, (kb | kk) != 0);
+        umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_lo + o), idesc, 1u);
+        umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_hi + o), idesc, 1u);
+      }
+      umma_commit(&empty[s]);                             // frees the stage when these MMAs have read it
+    }
+    umma_commit(done);                                    // accumulator complete
+  }
+
+  // ---- epilogue: all four warps, warp w owns TMEM lanes [32w, 32w + 32)
+  __syncwarp();
+  mbar_wait(done, 0);
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  float* yrow = Y + (size_t)(p0 + warp * 32 + lane) * ldy;
+#pragma unroll 1
+  for (int c = 0; c < TC_BN / 32; ++c) {
+    uint32_t v[32];
+    const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+        "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+          "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+          "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+          "=r"(v[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    const int mc = m0 + c * 32;
+#pragma unroll
+    for (int j = 0; j < 32; j += 4) {
+      if (mc + j < M)                                     // M (= ldy) is a multiple of 32
+        *reinterpret_cast<float4*>(yrow + mc + j) =
+            make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
+}
+
+}  // namespace pasif_tc

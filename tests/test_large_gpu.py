@@ -102,3 +102,36 @@ def test_several_chain_instances_ragged_tiles(prec):
     assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
     red = np.asarray(a["_p"]._getGradientReduced(0))
     assert rel_err(red, a["gradient"].reshape(19, na).sum(axis=0)) < (1e-12 if prec == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_stage_path_two_overlapping_parts(prec):
+    """> 256 trajectories: the dense-operator path splits the batch into two parts on two streams (GEMM of one part
+    overlaps the update of the other); the result is the same as with overlap=off (bit for bit) and matches the oracle."""
+    case = chain_case(32, True, E=300, L=60)
+    a = run_case(capi.engine_class(prec), case)
+    s = run_case(capi.engine_class(prec), case, options={"overlap": "off"})
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("large_stage_classes") >= 1
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    for key in ("amplitudes", "trajectory", "gradient"):
+        assert np.array_equal(a[key], s[key]), key
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("shape", [(100, 300), (514, 256), (66, 1000)])
+def test_stage_gemm_kernels_against_numpy(shape):
+    """The three GEMM kernels of the dense-operator path in isolation: DMMA is exact to fp64 round-off; both 3xTF32
+    kernels (mma.sync and tcgen05/TMEM/TMA) reach fp32-level accuracy and agree with each other."""
+    N, P = shape
+    rng = np.random.default_rng(N)
+    kd, x = rng.standard_normal((N, N)), rng.standard_normal((P, N))
+    ref = x @ kd.T
+    scale = np.max(np.abs(ref))
+    assert np.max(np.abs(capi.debug_gemm(kd, x, "f64", 0) - ref)) < 1e-13 * scale
+    y_mma, y_tc = capi.debug_gemm(kd, x, "f32", 0), capi.debug_gemm(kd, x, "f32", 1)
+    assert np.max(np.abs(y_mma - ref)) < 1e-5 * scale
+    assert np.max(np.abs(y_tc - ref)) < 1e-5 * scale
+    assert np.max(np.abs(y_tc - y_mma)) < 2e-6 * scale

@@ -28,7 +28,7 @@ def main():
         j = wl.chain_jacobian(s, 4)
         ff, fb = flops(s, j)
         for prec in ("f64", "f32"):
-            for opts in ([{}] if not dense else [{}, {"gemm": "off"}]):
+            for opts in ([{}] if not dense else ([{}, {"gemm": "tile"}] if prec == "f64" else [{}, {"tcgen05": "off"}, {"gemm": "tile"}])):
                 p = frontend.make_frontend(capi.engine_class(prec))(exc, 16000, 0)
                 for k, v in opts.items():
                     p._setOption(k, v)
@@ -44,6 +44,12 @@ def main():
                     p._getGradient(0, fetch=False)
                     res["grad_ms"] = p._query("last_device_ms")
                     res["gfwd_ms"], res["bwd_ms"] = p._query("ms_gfwd"), p._query("ms_bwd")
+                p._setOption("profile", "off")
+                for rep in range(2):
+                    p._getAmplitudes(fetch=False)
+                    res["fwd_ovl_ms"] = p._query("last_device_ms")
+                    p._getGradient(0, fetch=False)
+                    res["grad_ovl_ms"] = p._query("last_device_ms")
                 nsp = int(np.sqrt(L)); c = int(np.ceil(L / nsp))
                 fwd_tf = E * L * ff / (res["fwd_ms"] * 1e-3) / 1e12
                 gf_tf = E * (2 * L - c) * ff / (res["gfwd_ms"] * 1e-3) / 1e12
@@ -53,6 +59,7 @@ def main():
                 bw_gbs = E * (L - c) * NR * sz / (res["bwd_ms"] * 1e-3) / 1e9
                 print(f"ndof={ndof} dense={dense} {prec} {opts} N={s['n']} NA={j['n']} E={E} L={L} setup={ts:.1f}s gemm_classes={int(p._query('large_gemm_classes'))} "
                       f"F_fwd={ff} F_bwd={fb} | fwd {res['fwd_ms']:.1f} ms = {E*L/(res['fwd_ms']*1e-3):.3e} traj-steps/s {fwd_tf:.2f} TF | "
+                      f"OVERLAPPED fwd {res['fwd_ovl_ms']:.1f} ms = {E*L/(res['fwd_ovl_ms']*1e-3):.3e} traj-steps/s, grad {res['grad_ovl_ms']:.1f} ms = {E/(res['grad_ovl_ms']*1e-3):.3e} evals/s | "
                       f"grad {res['grad_ms']:.1f} ms gfwd {res['gfwd_ms']:.1f} ({gf_tf:.2f} TF) bwd {res['bwd_ms']:.1f} ({bw_tf:.2f} TF, {bw_gbs:.0f} GB/s read)", flush=True)
                 p.close() if hasattr(p, "close") else None
 
