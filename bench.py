@@ -391,9 +391,36 @@ def main():
                          "avg_launch_ms": k_ms[k] / max(k_launch[k], 1)}
     dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_step"])
     sz = 4 if w["dtype"] == "f32" else 8
+    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
+    stage = large and p._query("large_stage_classes") > 0
+    tensor = None
+    if stage:
+        # dense-operator path: the profiled kinds time the per-stage GEMM launches only (one GEMM per RK4 stage).
+        # 3xTF32 issues three tensor-core products per useful one.
+        pad = lambda n, m: (n + m - 1) // m * m
+        mult = 3 if w["dtype"] == "f32" else 1
+        ppad = pad(pairs, 128)
+        gemm_flops = {"gfwd": 2.0 * pad(N_FWD, 32) ** 2 * ppad * mult, "bwd": 2.0 * pad(N_ADJ, 32) ** 2 * ppad * mult}
+        if w["dtype"] == "f32":
+            tpeak = peaks.get("bf16_tflops", 1590.0) / 2.0
+            tsrc = "tf32 dense = half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2" if peaks else "fallback 1590 / 2"
+            tname = "sgemm_tn_3xtf32_tcgen05_kernel (tcgen05.mma kind::tf32, TMEM accumulator, TMA operands)"
+        else:
+            tpeak = capi.fma_peak(local_rank, "dmma")
+            tsrc = "register-resident mma.sync.m8n8k4.f64 microbenchmark, same run (tcgen05 has no fp64 kind)"
+            tname = "dgemm_tn_dmma_kernel (mma.sync.m8n8k4.f64, cp.async pipeline)"
+        ach = gemm_flops[dom] / (per_kernel[dom]["avg_launch_ms"] * 1e-3) / 1e12
+        tensor = {"bound": "tensor", "kernel": tname, "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
+                  "traffic": None, "peak_source": tsrc, "tensor_products_per_useful_product": mult,
+                  "useful_tflops": ach / mult, "gemm_us_per_launch": per_kernel[dom]["avg_launch_ms"] * 1e3,
+                  "gemm_share_of_step": (k_ms["gfwd"] + k_ms["bwd"]) / max(serial_ms, 1e-9),
+                  "whole_step": {"achieved": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12,
+                                 "frac": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12 / (tpeak / mult)},
+                  "per_kernel": per_kernel, "serialised_ms_per_step": serial_ms / a.steps,
+                  "note": "per-GEMM time from a serialised pass (profile=on); value/whole_step from the overlapped two-part schedule; "
+                          "whole_step.frac is against peak / tensor_products_per_useful_product"}
     # chunk-trajectory traffic: needed forward variables written once (recompute) and read once (adjoint)
     hbm_bytes = pairs * (L - c) * 2 * N_NEEDED * sz + pairs * nsp * (N_NEEDED if large else N_FWD) * sz * 2
-    peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     line = {
         "metric": "fwd+adjoint gradient evals/s", "value": value, "unit": "gradient evals/s", "n_gpus": world,
@@ -425,6 +452,12 @@ def main():
                 "d2h_bytes_per_step": int(pairs * N_ADJ * sz), "host_buffers": "pageable numpy arrays through the C ABI"},
         "gpu_launches": launches, "clocks": clocks, "wall_s_grad_steps": wall_grad,
     }
+    if tensor is not None:
+        line["roofline_fma"] = line["roofline"]
+        line["roofline"] = tensor
+        line["forward"]["roofline"] = {"bound": "tensor", "achieved": line["forward"]["roofline"]["achieved"], "unit": "TFLOP/s",
+                                       "peak": tensor["peak"] / tensor["tensor_products_per_useful_product"],
+                                       "frac": line["forward"]["roofline"]["achieved"] / (tensor["peak"] / tensor["tensor_products_per_useful_product"])}
     if not a.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
         v, fv, sample, _ = cpu_baseline_sample(w, threads)

@@ -42,15 +42,15 @@ struct UpdArgs {
   T h, h2, h6;
 };
 
-// grid (ceil(n_traj / U), NR / UPD_ROWS): a CTA of UPD_ROWS threads = UPD_ROWS consecutive rows of U trajectories
-constexpr int UPD_ROWS = 32;
+// grid (ceil(n_traj / (U * UPD_TG)), NR / 32), block (32, UPD_TG): a warp = 32 consecutive rows of U trajectories
+constexpr int UPD_TG = 8;
 
 template <typename T, int U>
-__global__ void __launch_bounds__(UPD_ROWS, 16) stage_update_kernel(const UpdArgs<T> a) {
+__global__ void __launch_bounds__(32 * UPD_TG) stage_update_kernel(const UpdArgs<T> a) {
   const Tables& tb = a.tb;
   const int NR = tb.NR, NPR = tb.NPR;
-  const int r = blockIdx.y * UPD_ROWS + threadIdx.x;
-  const long long p0 = (long long)blockIdx.x * U;
+  const int r = blockIdx.y * 32 + threadIdx.x;
+  const long long p0 = ((long long)blockIdx.x * UPD_TG + threadIdx.y) * U;
   if (p0 >= a.n_traj) return;
   const int4 w = __ldg(tb.widths + (r >> 5));
   const T* X = a.X + p0 * NR;
