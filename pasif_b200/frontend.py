@@ -19,8 +19,7 @@ import copy as cp
 import os
 
 import numpy as np
-from scipy.sparse import coo_matrix, dia_matrix
-from scipy.sparse.linalg import inv
+from scipy.sparse import coo_matrix, csc_matrix, dia_matrix
 
 
 class coo_tensor:
@@ -162,8 +161,7 @@ def make_frontend(driver_cls):
             self.system_initialConditions = np.concatenate([np.asarray(f, dtype=np.float64) for f in vecInitialConditions])
 
             # -M^-1 pre-scaling (PASIf.py:607-618)
-            self.system_M = -1. * inv(self.system_M.tocsc()) if N > 1 else -1. * inv(self.system_M)
-            minv = np.asarray(self.system_M.data, dtype=np.float64).reshape(-1)
+            self.system_M, minv = _neg_inverse_of_diagonal(diagM)
             self.system_B = coo_matrix(self.system_M.dot(self.system_B))
             self.system_K = coo_matrix(self.system_M.dot(self.system_K))
             _scale_tensor(self.system_Gamma, minv)
@@ -211,8 +209,7 @@ def make_frontend(driver_cls):
             self.jacobian_initialConditions = np.concatenate([np.asarray(f, dtype=np.float64) for f in vecInitialConditions])
 
             # -M^-1 pre-scaling; the adjoint force pattern is NOT scaled (PASIf.py:620-633)
-            self.jacobian_M = -1 * inv(self.jacobian_M.tocsc()) if A > 1 else -1 * inv(self.jacobian_M)
-            minv = np.asarray(self.jacobian_M.data, dtype=np.float64).reshape(-1)
+            self.jacobian_M, minv = _neg_inverse_of_diagonal(diagM)
             self.jacobian_B = coo_matrix(self.jacobian_M.dot(self.jacobian_B))
             self.jacobian_K = coo_matrix(self.jacobian_M.dot(self.jacobian_K))
             _scale_tensor(self.jacobian_Gamma, minv)
@@ -305,6 +302,20 @@ def make_frontend(driver_cls):
 
     PASIf.__name__ = "PASIf"
     return PASIf
+
+
+def _neg_inverse_of_diagonal(diag):
+    """-M^-1 of the (diagonal) global mass matrix as a sparse matrix + its diagonal (PASIf.py:609,627 call
+    ``scipy.sparse.linalg.inv``, a SuperLU solve against the identity column by column: O(N) Python-level solves,
+    87 s for the 4096-system config).  For a diagonal matrix that solve is ``1.0 / d`` per entry, which is what is
+    computed here (element-identical: tests/test_frontend.py compares the hand-off with the reference front end).
+    A zero mass entry is singular for the reference as well (SuperLU raises) and is rejected here."""
+    diag = np.asarray(diag, dtype=np.float64).reshape(-1)
+    if not np.all(diag != 0.0):
+        raise RuntimeError("Factor is exactly singular")
+    minv = -1. * (1.0 / diag)
+    n = diag.size
+    return csc_matrix((minv, np.arange(n), np.arange(n + 1)), shape=(n, n)), minv
 
 
 def _scale_tensor(t, minv):
