@@ -354,16 +354,24 @@ def main():
     clocks = sampler.stop()
     # ---------------- e2e: host buffers in, host result out, every step
     e2e_t = 0.0
+    e2e_parts = {"load_excitations_ms": 0.0, "h2d_staging_ms": 0.0, "gradient_call_ms": 0.0, "device_ms": 0.0, "d2h_staging_ms": 0.0}
     for i in range(1 + a.steps):
         barrier()
         t0 = time.time()
         p._loadExcitationsSet(exc, 16000)
+        t1 = time.time()
         g = p._getGradient(0)
+        t2 = time.time()
         if dist is not None:
             dist.all_reduce(red)
             torch.cuda.synchronize()
         if i > 0:
             e2e_t += time.time() - t0
+            e2e_parts["load_excitations_ms"] += (t1 - t0) * 1e3 / a.steps
+            e2e_parts["gradient_call_ms"] += (t2 - t1) * 1e3 / a.steps
+            e2e_parts["device_ms"] += p._query("last_device_ms") / a.steps
+            e2e_parts["h2d_staging_ms"] += p._query("last_h2d_ms") / a.steps
+            e2e_parts["d2h_staging_ms"] += p._query("last_d2h_ms") / a.steps
     tmax = torch.tensor([dev_ms, fwd_ms, e2e_t, wall_grad], dtype=torch.float64, device=f"cuda:{local_rank}")
     if dist is not None:
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
@@ -449,7 +457,8 @@ def main():
                          "note": "algorithmic chunk-trajectory + checkpoint bytes of the whole gradient step over its device time",
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "e2e": {"value": e2e_value, "unit": "gradient evals/s", "h2d_bytes_per_step": int(exc.nbytes),
-                "d2h_bytes_per_step": int(pairs * N_ADJ * sz), "host_buffers": "pageable numpy arrays through the C ABI"},
+                "d2h_bytes_per_step": int(pairs * N_ADJ * sz), "host_buffers": "pageable numpy arrays through the C ABI, staged through two pinned slots inside the engine",
+                "ms_per_step": e2e_t / a.steps * 1e3, "parts": e2e_parts},
         "gpu_launches": launches, "clocks": clocks, "wall_s_grad_steps": wall_grad,
     }
     if tensor is not None:

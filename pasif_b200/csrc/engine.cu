@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <time.h>
 
 #include <algorithm>
 #include <cstdlib>
@@ -332,6 +333,24 @@ struct DevBuf {
   }
 };
 
+// page-locked host staging area: user buffers are pageable (NumPy arrays, std::vector); copying through two pinned
+// slots keeps the DMA engine busy while the host thread fills / drains the other slot
+struct PinnedBuf {
+  void* p = nullptr;
+  size_t cap = 0;
+  void reserve(size_t bytes) {
+    if (bytes <= cap) return;
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+    CUDA_CHECK(cudaHostAlloc(&p, bytes, cudaHostAllocDefault));
+    cap = bytes;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr; cap = 0;
+  }
+};
+
 struct LargeClass;
 struct LargeClassDeleter { void operator()(LargeClass* p) const; };
 
@@ -350,14 +369,17 @@ struct pasif_engine {
   int dtype = PASIF_F64, device = 0;
   bool host_only = false;
   uint32_t E = 0, L = 0, sample_rate = 1, numsteps = 0;
-  std::vector<double> exc_host;
+  bool have_exc = false;
   SystemData fwd, bwd;
   std::vector<double> interp_table, modulation;
   uint32_t interp_window = 0;
   std::vector<DevClass> fwd_classes, joint_classes;
   bool fwd_ready = false, joint_ready = false;
   bool exc_dirty = true;
-  DevBuf d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;
+  DevBuf d_raw, d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;   // d_raw: excitations as handed over, [E][L] doubles
+  PinnedBuf h_stage;                               // 2 slots of kStageSlot bytes
+  cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  double last_h2d_ms = 0, last_d2h_ms = 0;         // host wall time of the last staged upload / download
   long long exc_rows = 0;
   bool exc_half = false;
   cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: adjoint sweep of chunk k overlaps the recompute of chunk k-1
@@ -597,11 +619,8 @@ template <typename T>
 void ensure_excitations(pasif_engine& E) {
   const bool half = E.interp_window != 0;
   if (!E.exc_dirty && half == E.exc_half) return;
-  if (E.exc_host.empty()) throw std::runtime_error("no excitation set loaded");
-  DevBuf raw;
-  const size_t raw_bytes = (size_t)E.E * E.L * sizeof(double);
-  raw.reserve(raw_bytes);
-  CUDA_CHECK(cudaMemcpyAsync(raw.p, E.exc_host.data(), raw_bytes, cudaMemcpyHostToDevice, E.stream));
+  if (!E.have_exc) throw std::runtime_error("no excitation set loaded");
+  DevBuf& raw = E.d_raw;                           // uploaded by load_exc (stream-ordered before the kernels below)
   if (!half) {
     const long long rows = (long long)std::max(E.L, E.numsteps) + 8;
     E.d_exc.reserve((size_t)rows * E.E * sizeof(T));
@@ -626,8 +645,6 @@ void ensure_excitations(pasif_engine& E) {
     E.exc_rows = U;
   }
   CUDA_CHECK(cudaGetLastError());
-  CUDA_CHECK(cudaStreamSynchronize(E.stream));
-  raw.release();
   E.exc_dirty = false;
   E.exc_half = half;
 }
@@ -668,17 +685,61 @@ void end_timing(pasif_engine& E) {
   }
 }
 
+constexpr size_t kStageSlot = 8u << 20;
+
+double wall_ms() {
+  timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return ts.tv_sec * 1e3 + ts.tv_nsec * 1e-6;
+}
+
+// host (pageable) -> device through the two pinned slots, stream-ordered on E.stream; returns without waiting for the
+// last DMA (consumers are launched on the same stream)
+void h2d_staged(pasif_engine& E, void* dst, const void* src, size_t bytes) {
+  const double t0 = wall_ms();
+  E.h_stage.reserve(2 * kStageSlot);
+  size_t i = 0;
+  for (size_t off = 0; off < bytes; off += kStageSlot, ++i) {
+    const size_t len = std::min(kStageSlot, bytes - off);
+    const int slot = (int)(i & 1);
+    char* h = (char*)E.h_stage.p + slot * kStageSlot;
+    CUDA_CHECK(cudaEventSynchronize(E.ev_stage[slot]));          // the DMA that last read this slot has finished
+    std::memcpy(h, (const char*)src + off, len);
+    CUDA_CHECK(cudaMemcpyAsync((char*)dst + off, h, len, cudaMemcpyHostToDevice, E.stream));
+    CUDA_CHECK(cudaEventRecord(E.ev_stage[slot], E.stream));
+  }
+  E.last_h2d_ms = wall_ms() - t0;
+}
+
+// device -> host (pageable doubles): DMA of chunk i+1 into one pinned slot overlaps the widening copy of chunk i out of
+// the other.  The reference returns `reel` values widened to Python floats (src/PASIfgpu.cpp:100-104); so does this.
 template <typename T>
 void download(pasif_engine& E, const void* dev, double* out, uint64_t n) {
-  if (!out) return;
-  if (sizeof(T) == sizeof(double)) {
-    CUDA_CHECK(cudaMemcpy(out, dev, n * sizeof(double), cudaMemcpyDeviceToHost));
-  } else {
-    std::vector<T> tmp(n);
-    CUDA_CHECK(cudaMemcpy(tmp.data(), dev, n * sizeof(T), cudaMemcpyDeviceToHost));
-    for (uint64_t i = 0; i < n; ++i) out[i] = (double)tmp[i];
+  if (!out || n == 0) return;
+  const double t0 = wall_ms();
+  E.h_stage.reserve(2 * kStageSlot);
+  const uint64_t per = kStageSlot / sizeof(T);
+  const uint64_t chunks = (n + per - 1) / per;
+  for (int s = 0; s < 2; ++s) CUDA_CHECK(cudaEventSynchronize(E.ev_stage[s]));
+  auto issue = [&](uint64_t c) {
+    const uint64_t len = std::min(per, n - c * per);
+    const int slot = (int)(c & 1);
+    CUDA_CHECK(cudaMemcpyAsync((char*)E.h_stage.p + slot * kStageSlot, (const T*)dev + c * per, len * sizeof(T),
+                               cudaMemcpyDeviceToHost, E.stream));
+    CUDA_CHECK(cudaEventRecord(E.ev_stage[slot], E.stream));
+  };
+  issue(0);
+  for (uint64_t c = 0; c < chunks; ++c) {
+    if (c + 1 < chunks) issue(c + 1);
+    const int slot = (int)(c & 1);
+    CUDA_CHECK(cudaEventSynchronize(E.ev_stage[slot]));
+    const T* h = (const T*)((const char*)E.h_stage.p + slot * kStageSlot);
+    const uint64_t len = std::min(per, n - c * per);
+    double* o = out + c * per;
+    if (sizeof(T) == sizeof(double)) std::memcpy(o, h, len * sizeof(double));
+    else for (uint64_t i = 0; i < len; ++i) o[i] = (double)h[i];
   }
-  (void)E;
+  E.last_d2h_ms = wall_ms() - t0;
 }
 
 // ---- getAmplitudes / getTrajectory
@@ -879,13 +940,21 @@ void set_csr(SystemData& s, uint32_t n_rows, uint32_t n_cols, const double* valu
 void load_exc(pasif_engine& E, const double* exc, uint32_t n_exc, uint32_t length, uint32_t sample_rate) {
   if (!exc || n_exc == 0 || length == 0) throw std::runtime_error("excitation set must be a non-empty [E][L] array");
   if (sample_rate == 0) throw std::runtime_error("sampleRate must be > 0");
-  if (!E.exc_host.empty() && n_exc != E.E && (E.fwd_ready || E.joint_ready)) {
+  if (E.have_exc && n_exc != E.E && (E.fwd_ready || E.joint_ready)) {
     // trajectory count changes: classes keep per-instance tables only, so nothing to rebuild except n_traj
     for (auto* v : {&E.fwd_classes, &E.joint_classes})
       for (auto& c : *v) c.n_traj = (long long)c.h.n_inst * n_exc;
   }
   E.E = n_exc; E.L = length; E.sample_rate = sample_rate;
-  E.exc_host.assign(exc, exc + (size_t)n_exc * length);
+  if (!E.host_only) {
+    // straight to the device, as the reference does (src/__GpuDriver.cu:343-381), but through pinned staging and
+    // without a host-side copy; the layout/precision pass runs on the device before the next solve
+    CUDA_CHECK(cudaSetDevice(E.device));
+    const size_t bytes = (size_t)n_exc * length * sizeof(double);
+    E.d_raw.reserve(bytes);
+    h2d_staged(E, E.d_raw.p, exc, bytes);
+  }
+  E.have_exc = true;
   E.exc_dirty = true;
 }
 
@@ -935,6 +1004,7 @@ int pasif_create(pasif_engine** out, const double* excitations, uint32_t n_excit
         CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_rec[i], cudaEventDisableTiming));
         CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_bwd[i], cudaEventDisableTiming));
       }
+      for (int i = 0; i < 2; ++i) CUDA_CHECK(cudaEventCreateWithFlags(&e->ev_stage[i], cudaEventDisableTiming));
       CUDA_CHECK(cudaEventCreate(&e->ev0));
       CUDA_CHECK(cudaEventCreate(&e->ev1));
     }
@@ -953,12 +1023,15 @@ void pasif_destroy(pasif_engine* e) {
     cudaSetDevice(e->device);
     free_classes(e->fwd_classes);
     free_classes(e->joint_classes);
-    for (DevBuf* b : {&e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
+    for (DevBuf* b : {&e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
     for (int i = 0; i < 2; ++i) {
       if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
     }
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    e->h_stage.release();
+    for (int i = 0; i < 2; ++i) if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
     for (cudaEvent_t ev : e->prof_events) cudaEventDestroy(ev);
     if (e->ev0) cudaEventDestroy(e->ev0);
     if (e->ev1) cudaEventDestroy(e->ev1);
@@ -1128,6 +1201,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "joint_instances") *value = inst(e->joint_classes);
   else if (k == "last_device_ms") *value = e->last_ms;
   else if (k == "last_launches") *value = (double)e->last_launches;
+  else if (k == "last_h2d_ms") *value = e->last_h2d_ms;
+  else if (k == "last_d2h_ms") *value = e->last_d2h_ms;
   else if (k == "jit_compiles") *value = (double)e->jit_compiles;
   else if (k == "jit_cache_hits") *value = (double)e->jit_cache_hits;
   else if (k == "aot_hits") *value = (double)e->aot_hits;
