@@ -237,6 +237,10 @@ def main():
     ap.add_argument("--dtype", default="", choices=["", "f32", "f64"], help="override the workload's compute type")
     ap.add_argument("--excitations", type=int, default=0, help="override the number of excitations (debug)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--compat", default="reference", choices=["reference", "clean"],
+                    help="adjoint schedule: the reference's literal one (default, parity with its outputs) or the exact "
+                         "discrete adjoint, whose chunk trajectories are kept from the forward sweep as far as HBM allows")
+    ap.add_argument("--tail-budget-gb", default="auto", help="clean schedule: device memory for kept chunk trajectories")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
     if a.systems:
@@ -287,6 +291,8 @@ def main():
     fe._local_rank = lambda: local_rank
     p = Local(exc, 16000, 0)
     fe._local_rank = saved
+    p._setOption("compat", a.compat)
+    p._setOption("tail_budget_gb", a.tail_budget_gb)
     t_setup = time.time()
     p.setSystems(*wl.to_frontend_args(systems, mod))
     p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
@@ -386,9 +392,18 @@ def main():
     fwd_value = tot_pairs * L * a.steps / (fwd_ms * 1e-3)
     e2e_value = tot_pairs * a.steps / e2e_t
     nsp, c = schedule(L, w["dtype"])
-    # literal reference schedule: forward sweep n steps + recompute (n - c) steps; adjoint (n - c) steps (chunk 0 skipped)
-    flops_gfwd = pairs * (2 * L - c) * F_FWD
-    flops_bwd = pairs * (L - c) * F_BWD
+    stored_chunks = 0
+    if a.compat == "reference":
+        # literal reference schedule: forward sweep n steps + recompute (n - c) steps; adjoint (n - c) steps (chunk 0 skipped)
+        steps_gfwd, steps_bwd = 2 * L - c, L - c
+    else:
+        # exact schedule: sweep n steps, recompute only the chunks whose trajectory did not fit in HBM, adjoint n steps
+        c = int(np.ceil(np.sqrt(L)))
+        nsp = (L + c - 1) // c
+        stored_chunks = int(p._query("stored_chunks"))
+        steps_gfwd, steps_bwd = L + min(L, (nsp - stored_chunks) * c), L
+    flops_gfwd = pairs * steps_gfwd * F_FWD
+    flops_bwd = pairs * steps_bwd * F_BWD
     fma = {"f64": capi.fma_peak(local_rank, "f64"), "f32": capi.fma_peak(local_rank, "f32")}
     peak = fma[w["dtype"]]
     per_kernel = {}
@@ -428,13 +443,15 @@ def main():
                   "note": "per-GEMM time from a serialised pass (profile=on); value/whole_step from the overlapped two-part schedule; "
                           "whole_step.frac is against peak / tensor_products_per_useful_product"}
     # chunk-trajectory traffic: needed forward variables written once (recompute) and read once (adjoint)
-    hbm_bytes = pairs * (L - c) * 2 * N_NEEDED * sz + pairs * nsp * (N_NEEDED if large else N_FWD) * sz * 2
+    hbm_bytes = pairs * steps_bwd * 2 * N_NEEDED * sz + pairs * nsp * (N_NEEDED if large else N_FWD) * sz * 2
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
     line = {
         "metric": "fwd+adjoint gradient evals/s", "value": value, "unit": "gradient evals/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": w["dtype"], "data": "synthetic",
-        "config": {"workload": w["name"], "systems_per_gpu": S, "excitations": E, "rk4_steps": L, "compat": "reference",
+        "config": {"workload": w["name"], "systems_per_gpu": S, "excitations": E, "rk4_steps": L, "compat": a.compat,
+                   "schedule": {"chunks": nsp, "chunk_steps": c, "chunks_kept_in_hbm": stored_chunks,
+                                "forward_steps_per_eval": steps_gfwd, "adjoint_steps_per_eval": steps_bwd},
                    "l2": "working set (checkpoints + chunk trajectory, > 1 GB) exceeds the 126 MB L2; no flush needed",
                    "timing": "CUDA events on the engine stream, summed over the timed steps, max over ranks",
                    "setup_s": t_setup},

@@ -376,6 +376,9 @@ struct pasif_engine {
   std::vector<DevClass> fwd_classes, joint_classes;
   bool fwd_ready = false, joint_ready = false;
   bool exc_dirty = true;
+  DevBuf d_tail;                                  // clean schedule: chunk trajectories kept from the forward sweep (sized to HBM)
+  double tail_budget_gb = -1;                     // < 0: automatic (a fraction of the free device memory); 0: off
+  long long last_stored_chunks = 0, last_chunks = 0;
   DevBuf d_raw, d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;   // d_raw: excitations as handed over, [E][L] doubles
   PinnedBuf h_stage;                               // 2 slots of kStageSlot bytes
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
@@ -825,6 +828,29 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
       E.d_ckpt.reserve((size_t)(nsp + 1) * slot_elems * sizeof(T));
       E.d_dense.reserve(std::max<size_t>((size_t)chunk * NV * P, 1) * sizeof(T));
       T* ckpt = (T*)E.d_ckpt.p;
+      // Schedule sized to HBM (exact schedule only): the chunk trajectories of the LAST chunks -- the first ones the
+      // adjoint sweep consumes -- are written by the forward sweep itself into whatever device memory is free, so those
+      // chunks need no recompute launch.  In the literal reference schedule the replayed chunk is not the swept
+      // trajectory (quirk A1: replay starts one sample late), so there every chunk has to be recomputed.
+      long long sp_store = nsp;                    // chunks [sp_store, nsp) are stored by the sweep
+      // automatic sizing keeps chunks only when the batch saturates the GPU (>= 8 warps per SM): a small batch is
+      // latency-bound, its recompute already runs for free beside the adjoint sweep on the second stream, and reading the
+      // kept trajectory from HBM instead of the L2-resident chunk buffer would slow it down (C2: 57 ms vs 42 ms)
+      const bool tail_wanted = E.tail_budget_gb > 0 || (E.tail_budget_gb < 0 && P >= 256ll * E.n_sm);
+      if (E.compat_clean && tail_wanted) {
+        const bool ovl_ = E.overlap && !E.profile;
+        if (ovl_) E.d_dense2.reserve(std::max<size_t>((size_t)chunk * NV * P, 1) * sizeof(T));   // count it before sizing
+        size_t free_b = 0, total_b = 0;
+        CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
+        double budget = (double)(free_b + E.d_tail.cap) * 0.9;
+        if (E.tail_budget_gb > 0) budget = std::min(budget, E.tail_budget_gb * 1e9);
+        const double chunk_bytes = (double)chunk * NV * P * sizeof(T);
+        const long long fit = (long long)(budget / chunk_bytes);
+        sp_store = std::max<long long>(0, nsp - fit);
+        if (sp_store < nsp) E.d_tail.reserve((size_t)(n - sp_store * chunk) * NV * P * sizeof(T));
+      }
+      E.last_stored_chunks = nsp - sp_store;
+      E.last_chunks = nsp;
       // forward sweep with checkpoints
       {
         pasif::FwdArgs<T> a;
@@ -833,14 +859,25 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         a.save_ptr = ckpt; a.save_every = (int)chunk; a.save_layout = 0; a.save_slots = (int)nsp;
         if (!E.compat_clean) {
           a.save_phase = 0;                        // slot j <- state AFTER step j*c (quirk A1)
+          launch(E, c.k_gfwd, P, a, 1);
         } else {
           a.save_phase = 1;                        // slot j <- state BEFORE step j*c; slot 0 = initial condition
           const long long tot = (long long)NF * P;
           init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
               (const T*)c.ic.p, ckpt, NF, c.h.n_inst, (int)E.E, (int)P);
           ++E.last_launches;
+          const long long t_split = std::min<long long>(n, sp_store * chunk);
+          if (t_split > 0) {                       // checkpoints only
+            a.t1 = (int)t_split;
+            launch(E, c.k_gfwd, P, a, 1);
+          }
+          if (t_split < n) {                       // checkpoints + chunk trajectories, continuing from slot sp_store
+            a.q_in = ckpt + (size_t)sp_store * slot_elems;
+            a.t0 = (int)t_split; a.t1 = (int)n;
+            a.dense_ptr = (T*)E.d_tail.p;
+            launch(E, c.k_gfwd, P, a, 1);
+          }
         }
-        launch(E, c.k_gfwd, P, a, 1);
       }
       const long long first = E.compat_clean ? 0 : 1;      // the reference never back-propagates chunk 0 (quirk A2)
       // Two streams, two chunk-trajectory buffers: the recompute of chunk k-1 (stream) runs while the adjoint sweep of
@@ -858,14 +895,17 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         const long long len = end - start;
         if (len <= 0) continue;
         const int buf = (int)(it & 1);
-        if (ovl && it >= 2) CUDA_CHECK(cudaStreamWaitEvent(E.stream, E.ev_bwd[buf], 0));   // buffer consumed
+        const bool stored = sp >= sp_store;        // chunk trajectory already in d_tail (written by the sweep)
         pasif::FwdArgs<T> a;
         fill_common<T>(E, c, a);
-        a.q_in = ckpt + (size_t)sp * slot_elems;
-        a.t0 = (int)start; a.t1 = (int)end;
-        a.dense_ptr = dense_buf[buf];
-        launch(E, c.k_gfwd, P, a, 1, E.stream);
-        if (ovl) {
+        if (!stored) {
+          if (ovl && it >= 2) CUDA_CHECK(cudaStreamWaitEvent(E.stream, E.ev_bwd[buf], 0));   // buffer consumed
+          a.q_in = ckpt + (size_t)sp * slot_elems;
+          a.t0 = (int)start; a.t1 = (int)end;
+          a.dense_ptr = dense_buf[buf];
+          launch(E, c.k_gfwd, P, a, 1, E.stream);
+        }
+        if (ovl) {                                 // (for a stored chunk: orders the adjoint stream after the sweep)
           CUDA_CHECK(cudaEventRecord(E.ev_rec[buf], E.stream));
           CUDA_CHECK(cudaStreamWaitEvent(sB, E.ev_rec[buf], 0));
         }
@@ -873,7 +913,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         std::memset(&b, 0, sizeof b);
         b.coef = (const T*)c.coef_adj.p;
         b.lam = (T*)E.d_lam.p;
-        b.dense = dense_buf[buf];
+        b.dense = stored ? (const T*)E.d_tail.p + (size_t)(start - sp_store * chunk) * NV * P : dense_buf[buf];
         // state standing in for index -1: the reference reads the PREVIOUS chunk's checkpoint slot (quirk A4);
         // the exact sweep uses this chunk's own start state
         b.prev = ckpt + (size_t)(E.compat_clean ? sp : sp - 1) * slot_elems;
@@ -1023,7 +1063,7 @@ void pasif_destroy(pasif_engine* e) {
     cudaSetDevice(e->device);
     free_classes(e->fwd_classes);
     free_classes(e->joint_classes);
-    for (DevBuf* b : {&e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
+    for (DevBuf* b : {&e->d_tail, &e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
     for (int i = 0; i < 2; ++i) {
       if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
@@ -1139,6 +1179,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->overlap = (v == "on" || v == "1");
   } else if (k == "profile") {
     e->profile = (v == "on" || v == "1");
+  } else if (k == "tail_budget_gb") {
+    e->tail_budget_gb = (v == "auto") ? -1.0 : std::atof(v.c_str());
   } else if (k == "numsteps") {
     e->numsteps = (uint32_t)std::strtoul(v.c_str(), nullptr, 10);
     e->exc_dirty = true;
@@ -1201,6 +1243,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "joint_instances") *value = inst(e->joint_classes);
   else if (k == "last_device_ms") *value = e->last_ms;
   else if (k == "last_launches") *value = (double)e->last_launches;
+  else if (k == "stored_chunks") *value = (double)e->last_stored_chunks;
+  else if (k == "chunks") *value = (double)e->last_chunks;
   else if (k == "last_h2d_ms") *value = e->last_h2d_ms;
   else if (k == "last_d2h_ms") *value = e->last_d2h_ms;
   else if (k == "jit_compiles") *value = (double)e->jit_compiles;

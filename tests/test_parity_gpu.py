@@ -95,6 +95,33 @@ def test_save_argument_stops_after_chunk():
         assert col_err(a._getGradient(save), b._getGradient(save), 6) < 1e-12
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_hbm_sized_schedule_is_bit_identical(prec):
+    """Exact schedule (compat=clean): chunk trajectories kept from the forward sweep in free device memory
+    (option tail_budget_gb: auto / a byte budget / 0 = always recompute) never change a bit of the result; only the
+    number of recompute launches changes."""
+    case = wl.golden_case("fit8x2_jit")
+    E = len(case["excitations"])
+    n = case["numsteps"] or len(case["excitations"][0])
+    chunk = int(np.ceil(np.sqrt(n)))
+    nsp = (n + chunk - 1) // chunk
+    chunk_gb = chunk * 4 * (2 * E) * (8 if prec == "f64" else 4) / 1e9           # NV = 4 needed forward variables
+    ref = run_case(capi.engine_class(prec, "clean"), case, want_traj=False, options={"tail_budget_gb": "0"})
+    assert ref["_p"]._query("stored_chunks") == 0 and ref["_p"]._query("chunks") == nsp
+    launches_ref = ref["_p"]._query("last_launches")
+    for budget, stored in ((repr(1e3 * chunk_gb * nsp), nsp), (repr(3.5 * chunk_gb), 3)):
+        out = run_case(capi.engine_class(prec, "clean"), case, want_traj=False, options={"tail_budget_gb": budget})
+        assert out["_p"]._query("stored_chunks") == stored
+        assert np.array_equal(out["gradient"], ref["gradient"])
+        assert out["_p"]._query("last_launches") < launches_ref
+    # automatic sizing leaves a batch too small to saturate the GPU on the (L2-resident) recompute path
+    auto = run_case(capi.engine_class(prec, "clean"), case, want_traj=False, options={"tail_budget_gb": "auto"})
+    assert auto["_p"]._query("stored_chunks") == 0 and np.array_equal(auto["gradient"], ref["gradient"])
+    # the literal reference schedule replays a shifted trajectory (quirk A1): nothing can be kept from the sweep
+    lit = run_case(capi.engine_class(prec, "reference"), case, want_traj=False)
+    assert lit["_p"]._query("stored_chunks") == 0
+
+
 def test_runtime_specialised_pattern_nvrtc():
     """A sparsity pattern with no prebuilt kernel goes through NVRTC (never a CPU or interpreted fallback)."""
     case = wl.golden_case("mixed2")
