@@ -45,9 +45,9 @@ WORKLOADS = {
     # config 4 (large-DOF shared-B batch): ONE 256-DOF chain (514 states, 518-state adjoint) x 16384 excitation replicas.
     # The rate is step-count independent; the step counts keep a bench step at a few seconds.
     "c4s": dict(kind="chain", dense=False, ndof=256, n_systems=1, E=16384, L=2000, dtype="f64", jitter_seed=None, exc_seed=5,
-                name="C4 sparse: 256-DOF oscillator chain (tridiagonal K, on-site Gamma/Lambda; 514 states) x 16384 excitations x 2000 RK4 steps, forward + adjoint (tile kernels, row programs)"),
+                name="C4 sparse: 256-DOF oscillator chain (tridiagonal K, on-site Gamma/Lambda; 514 states) x 16384 excitations x 2000 RK4 steps, forward + adjoint"),
     "c4d": dict(kind="chain", dense=True, ndof=256, n_systems=1, E=16384, L=128, dtype="f64", jitter_seed=None, exc_seed=5,
-                name="C4 dense: 256-DOF system with dense shared K, B (514 states) x 16384 excitations x 128 RK4 steps, forward + adjoint (tile kernels, tensor-core linear term)"),
+                name="C4 dense: 256-DOF system with dense shared K, B (514 states) x 16384 excitations x 128 RK4 steps, forward + adjoint"),
 }
 
 # algorithmic flops per trajectory-step of the 8-state system / 12-state Jacobian:
@@ -241,6 +241,7 @@ def main():
                     help="adjoint schedule: the reference's literal one (default, parity with its outputs) or the exact "
                          "discrete adjoint, whose chunk trajectories are kept from the forward sweep as far as HBM allows")
     ap.add_argument("--tail-budget-gb", default="auto", help="clean schedule: device memory for kept chunk trajectories")
+    ap.add_argument("--lanes", default="on", help="lane-block split of large components: on | off | widest group (8..128)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
     if a.systems:
@@ -293,6 +294,7 @@ def main():
     fe._local_rank = saved
     p._setOption("compat", a.compat)
     p._setOption("tail_budget_gb", a.tail_budget_gb)
+    p._setOption("lanes", a.lanes)
     t_setup = time.time()
     p.setSystems(*wl.to_frontend_args(systems, mod))
     p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
@@ -416,6 +418,10 @@ def main():
     sz = 4 if w["dtype"] == "f32" else 8
     peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json"))) if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else {}
     stage = large and p._query("large_stage_classes") > 0
+    lane = p._query("lane_classes") > 0
+    if lane:
+        # lane-block split: every lane writes / reads its share of the needed forward variables
+        N_NEEDED = int(p._query("lane_nv") * p._query("lane_G"))
     tensor = None
     if stage:
         # dense-operator path: the profiled kinds time the per-stage GEMM launches only (one GEMM per RK4 stage).
@@ -460,7 +466,7 @@ def main():
                     "roofline": {"bound": "fma", "achieved": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12,
                                  "peak": peak, "unit": "TFLOP/s",
                                  "frac": pairs * L * F_FWD / (fwd_ms / a.steps * 1e-3) / 1e12 / peak}},
-        "roofline": {"bound": "fma", "kernel": ({"gfwd": "large_forward_kernel", "bwd": "large_backward_kernel"} if large else {"gfwd": "pasif_gfwd_*", "bwd": "pasif_bwd_*"})[dom],
+        "roofline": {"bound": "fma", "kernel": ({"gfwd": "large_forward_kernel", "bwd": "large_backward_kernel"} if (large and not lane) else {"gfwd": "pasif_gfwd_*", "bwd": "pasif_bwd_*"})[dom],
                      "achieved": per_kernel[dom]["tflops"], "peak": peak, "unit": "TFLOP/s",
                      "frac": per_kernel[dom]["tflops"] / peak if per_kernel[dom]["tflops"] else None, "traffic": None,
                      "peak_source": "pasif_fma_peak register-resident FMA microbenchmark, same run (MEASURED_PEAKS.json has no FMA-pipe figure)",
@@ -478,6 +484,11 @@ def main():
                 "ms_per_step": e2e_t / a.steps * 1e3, "parts": e2e_parts},
         "gpu_launches": launches, "clocks": clocks, "wall_s_grad_steps": wall_grad,
     }
+    if lane:
+        line["config"]["lane_split"] = {k: p._query("lane_" + k) for k in ("G", "R", "RA", "nv", "nc_fwd", "nc_adj", "halo_fwd", "halo_adj", "halo_p", "efficiency")}
+        line["config"]["path"] = "lane-block register kernels (lane_split.hpp): G threads per trajectory, state in registers, halo exchange per stage"
+    elif large:
+        line["config"]["path"] = "dense-operator stage path (tensor-core GEMM per stage)" if stage else "shared-memory tile kernels"
     if tensor is not None:
         line["roofline_fma"] = line["roofline"]
         line["roofline"] = tensor

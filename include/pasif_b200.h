@@ -66,7 +66,9 @@ int pasif_set_interp(pasif_engine* e, const double* table, uint32_t table_len, u
 int pasif_set_modulation(pasif_engine* e, const double* buffer, uint32_t n);
 
 /* engine options (no reference counterpart): "compat" = "reference" | "clean" (adjoint schedule semantics),
- * "jit" = "on" | "off" (allow NVRTC specialisation for patterns without a prebuilt kernel), "block" = threads per CTA */
+ * "jit" = "on" | "off" (allow NVRTC specialisation for patterns without a prebuilt kernel), "block" = threads per CTA,
+ * "lanes" = "on" | "off" | widest thread group (8..128) of the lane-block split of large components,
+ * "large_threshold", "gemm", "tcgen05", "overlap", "profile", "tail_budget_gb", "numsteps" */
 int pasif_set_option(pasif_engine* e, const char* key, const char* value);
 
 /* _getAmplitudes (src/__GpuDriver.cu:416-461): out[e * N + i], n_out = N * E.  out == NULL runs the solve and keeps
@@ -89,6 +91,9 @@ int pasif_query(const pasif_engine* e, const char* key, double* value);
 /* C++ source of the compile-time pattern traits of the currently loaded systems (used by tools/gen_aot_patterns.py
  * to pre-build kernels); writes at most cap bytes incl. NUL, *needed = bytes required */
 int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* needed);
+/* NVRTC + ptxas -v logs of the run-time specialised kernels of the loaded classes, compiled for `arch` ("sm_100a");
+ * no device needed (debugging aid: register use of the lane-block kernels) */
+int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t cap, uint64_t* needed);
 /* device pipe microbenchmarks (register-resident, no memory traffic): achieved TFLOP/s.  dtype PASIF_F64 / PASIF_F32: FMA pipe;
  * 2: mma.sync m8n8k4 f64 (DMMA); 3: mma.sync m16n8k8 tf32 (fp32 accumulate) */
 int pasif_fma_peak(int device, int dtype, double* tflops);

@@ -20,7 +20,7 @@ pasif_set_fwd_k pasif_set_fwd_gamma pasif_set_fwd_lambda pasif_set_fwd_psi pasif
 pasif_set_bwd_k pasif_set_bwd_gamma pasif_set_bwd_lambda pasif_set_bwd_psi pasif_set_bwd_force pasif_set_bwd_ic pasif_alloc_adjoint
 pasif_set_interp pasif_set_modulation pasif_set_option
 pasif_get_amplitudes pasif_trajectory_size pasif_get_trajectory pasif_get_gradient pasif_get_gradient_reduced
-pasif_get_gradient_reduced_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm""".split()
+pasif_get_gradient_reduced_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm pasif_debug_jit_log""".split()
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -59,6 +59,7 @@ def lib():
         L.pasif_get_gradient_reduced_device.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
         L.pasif_query.argtypes = [C.c_void_p, C.c_char_p, _dp]
         L.pasif_emit_patterns.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
+        L.pasif_debug_jit_log.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.pasif_fma_peak.argtypes = [C.c_int, C.c_int, _dp]
         L.pasif_debug_gemm.argtypes = [C.c_int, C.c_int, C.c_int, C.c_uint32, C.c_uint64, _dp, _dp, _dp]
         _lib = L
@@ -206,6 +207,14 @@ class Engine:
         self._check(lib().pasif_emit_patterns(self._h, None, 0, C.byref(need)))
         buf = C.create_string_buffer(need.value)
         self._check(lib().pasif_emit_patterns(self._h, buf, need.value, C.byref(need)))
+        return buf.value.decode()
+
+    def jit_log(self, arch="sm_100a"):
+        """NVRTC + ptxas -v logs of the run-time specialised kernels of the loaded classes (no device needed)."""
+        need = C.c_uint64()
+        self._check(lib().pasif_debug_jit_log(self._h, arch.encode(), None, 0, C.byref(need)))
+        buf = C.create_string_buffer(need.value)
+        self._check(lib().pasif_debug_jit_log(self._h, arch.encode(), buf, need.value, C.byref(need)))
         return buf.value.decode()
 
 

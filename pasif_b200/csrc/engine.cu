@@ -26,6 +26,7 @@
 
 #include "../../include/pasif_b200.h"
 #include "pattern.hpp"
+#include "lane_split.hpp"
 #include "rk4_kernels.cuh"
 #include "large_kernels.cuh"
 #include "stage_kernels.cuh"
@@ -135,23 +136,27 @@ __global__ void prep_exc_half_kernel(const double* __restrict__ raw, const T* __
   out[idx] = v;
 }
 
+// G = lanes per trajectory (1 for ordinary classes): thread-trajectory p -> lane p % G of trajectory p / G = inst * E + e,
+// tables indexed by the virtual instance inst * G + lane (rk4_kernels.cuh, lane-block classes)
 template <typename T>
-__global__ void init_state_kernel(const T* __restrict__ ic, T* __restrict__ st, int N, int n_inst, int E, int n_traj) {
+__global__ void init_state_kernel(const T* __restrict__ ic, T* __restrict__ st, int N, int n_inst, int E, int n_traj, int G) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * n_traj) return;
   const int i = (int)(idx / n_traj);
   const int p = (int)(idx - (long long)i * n_traj);
-  st[idx] = ic[(long long)i * n_inst + p / E];
+  const int lane = p % G, traj = p / G;
+  st[idx] = ic[(long long)i * n_inst + (traj / E) * G + lane];
 }
 
 template <typename T>
 __global__ void scatter_user_kernel(const T* __restrict__ st, const int* __restrict__ varmap, T* __restrict__ out,
-                                    int N, int n_inst, int E, int n_traj, int n_glob) {
+                                    int N, int n_inst, int E, int n_traj, int n_glob, int G) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * n_traj) return;
   const int i = (int)(idx / n_traj);
   const int p = (int)(idx - (long long)i * n_traj);
-  const int inst = p / E, e = p - inst * E;
+  const int lane = p % G, traj = p / G;
+  const int e = traj % E, inst = (traj / E) * G + lane;
   const int g = varmap[(long long)i * n_inst + inst];
   if (g >= 0) out[(long long)e * n_glob + g] = st[idx];
 }
@@ -391,7 +396,11 @@ struct pasif_engine {
   bool overlap = true;
   std::string err;
   bool compat_clean = false, jit_on = true, gemm_on = true;
-  int large_threshold = 48;                      // components with more coupled variables use the tile kernels
+  int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
+  int lanes_max = 128;                           // widest thread group of the lane-block split (0: off)
+  long long lane_classes = 0;
+  LaneSplitReport lane_report;                   // of the last class that was split
+  std::string lane_reject;                       // why the last large class was not split
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
   bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
@@ -537,17 +546,19 @@ cudaEvent_t prof_event(pasif_engine& E, int kind) {
 
 // threads per CTA: the configured maximum while the grid still gives every SM >= 2 CTAs, else narrower CTAs so that
 // a small batch (config C2: 1024 trajectories) spreads over more SMs
-unsigned pick_block(const pasif_engine& E, long long n_threads) {
+unsigned pick_block(const pasif_engine& E, long long n_threads, unsigned min_block = 32) {
   unsigned block = (unsigned)E.block;
-  while (block > 32 && (n_threads + block - 1) / block < 2ll * E.n_sm) block >>= 1;
+  while (block > min_block && block > 32 && (n_threads + block - 1) / block < 2ll * E.n_sm) block >>= 1;
   return block < 32 ? 32 : block;
 }
 
 template <typename Args>
-void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& args, int kind, cudaStream_t st = nullptr) {
+void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& args, int kind, cudaStream_t st = nullptr,
+            int lanes = 1) {
   if (!k.valid()) throw std::runtime_error("internal: kernel handle not resolved");
   if (!st) st = E.stream;
-  const unsigned block = pick_block(E, n_threads);
+  // lane-block classes: a group of `lanes` threads must sit in one CTA; they are compiled for the full block
+  const unsigned block = lanes > 1 ? (unsigned)PASIF_BLOCK : pick_block(E, n_threads);
   const unsigned grid = (unsigned)((n_threads + block - 1) / block);
   void* params[] = {(void*)&args};
   if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), st));
@@ -586,6 +597,18 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
   for (size_t i = 0; i < cds.size(); ++i) {
     DevClass& dc = out[i];
     dc.h = std::move(cds[i]);
+    if (is_large(E, dc.h) && E.lanes_max >= 8) {
+      // lane-block split (lane_split.hpp): the component becomes n_inst * G virtual instances of one lane-local pattern
+      // that the register-resident kernels integrate with G threads per trajectory; components it does not suit
+      // (dense operators, irregular coupling) stay with the tile kernels / the dense-operator path below
+      ClassData split;
+      LaneSplitReport rep;
+      if (lane_split(dc.h, (int)sizeof(T), E.lanes_max, split, rep)) {
+        dc.h = std::move(split);
+        ++E.lane_classes;
+        E.lane_report = rep;
+      } else E.lane_reject = rep.why;
+    }
     dc.n_traj = (long long)dc.h.n_inst * E.E;
     if (dc.n_traj >= (1ll << 31)) throw std::runtime_error("more than 2^31 trajectories in one class");
     if (E.host_only) continue;
@@ -597,7 +620,7 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
       upload<T>(dc.ic_adj, dc.h.ic_adj);
       upload_int(dc.varmap_adj, dc.h.varmap_adj);
     }
-    if (is_large(E, dc.h)) build_large_class<T>(E, dc);
+    if (dc.h.lanes == 1 && is_large(E, dc.h)) build_large_class<T>(E, dc);
     else resolve_kernels(E, dc);
   }
 }
@@ -774,7 +797,7 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
     } else {
       a.final_user = (T*)E.d_user.p;
     }
-    launch(E, c.k_fwd, c.n_traj, a, 0);
+    launch(E, c.k_fwd, c.n_traj, a, 0, nullptr, c.h.lanes);
   }
   end_timing(E);
   download<T>(E, trajectory ? E.d_traj.p : E.d_user.p, out, trajectory ? n_slots * width : width);
@@ -811,7 +834,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     {
       const long long tot = (long long)NA * P;
       init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-          (const T*)c.ic_adj.p, (T*)E.d_lam.p, NA, c.h.n_inst, (int)E.E, (int)P);
+          (const T*)c.ic_adj.p, (T*)E.d_lam.p, NA, c.h.n_inst, (int)E.E, (int)P, c.h.lanes);
       ++E.last_launches;
     }
     if (n > 0) {
@@ -859,23 +882,23 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         a.save_ptr = ckpt; a.save_every = (int)chunk; a.save_layout = 0; a.save_slots = (int)nsp;
         if (!E.compat_clean) {
           a.save_phase = 0;                        // slot j <- state AFTER step j*c (quirk A1)
-          launch(E, c.k_gfwd, P, a, 1);
+          launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
         } else {
           a.save_phase = 1;                        // slot j <- state BEFORE step j*c; slot 0 = initial condition
           const long long tot = (long long)NF * P;
           init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-              (const T*)c.ic.p, ckpt, NF, c.h.n_inst, (int)E.E, (int)P);
+              (const T*)c.ic.p, ckpt, NF, c.h.n_inst, (int)E.E, (int)P, c.h.lanes);
           ++E.last_launches;
           const long long t_split = std::min<long long>(n, sp_store * chunk);
           if (t_split > 0) {                       // checkpoints only
             a.t1 = (int)t_split;
-            launch(E, c.k_gfwd, P, a, 1);
+            launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
           }
           if (t_split < n) {                       // checkpoints + chunk trajectories, continuing from slot sp_store
             a.q_in = ckpt + (size_t)sp_store * slot_elems;
             a.t0 = (int)t_split; a.t1 = (int)n;
             a.dense_ptr = (T*)E.d_tail.p;
-            launch(E, c.k_gfwd, P, a, 1);
+            launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
           }
         }
       }
@@ -903,7 +926,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
           a.q_in = ckpt + (size_t)sp * slot_elems;
           a.t0 = (int)start; a.t1 = (int)end;
           a.dense_ptr = dense_buf[buf];
-          launch(E, c.k_gfwd, P, a, 1, E.stream);
+          launch(E, c.k_gfwd, P, a, 1, E.stream, c.h.lanes);
         }
         if (ovl) {                                 // (for a stored chunk: orders the adjoint stream after the sweep)
           CUDA_CHECK(cudaEventRecord(E.ev_rec[buf], E.stream));
@@ -921,7 +944,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         b.alias_local = E.compat_clean ? -1000000 : (int)(S_global - sp);
         b.n_inst = c.h.n_inst; b.E = (int)E.E; b.n_traj = (int)P;
         b.h = a.h; b.h2 = a.h2; b.h6 = a.h6;
-        launch(E, c.k_bwd, P, b, 2, sB);
+        launch(E, c.k_bwd, P, b, 2, sB, c.h.lanes);
         if (ovl) CUDA_CHECK(cudaEventRecord(E.ev_bwd[buf], sB));
         last_buf = buf;
         ++it;
@@ -931,7 +954,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     }
     const long long tot = (long long)NA * P;
     scatter_user_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-        (const T*)E.d_lam.p, (const int*)c.varmap_adj.p, d_user_out, NA, c.h.n_inst, (int)E.E, (int)P, (int)E.bwd.n);
+        (const T*)E.d_lam.p, (const int*)c.varmap_adj.p, d_user_out, NA, c.h.n_inst, (int)E.E, (int)P, (int)E.bwd.n, c.h.lanes);
     ++E.last_launches;
   }
 }
@@ -1173,6 +1196,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->gemm_stage = (v != "tile");
   } else if (k == "tcgen05") {
     e->tcgen05_on = (v == "on" || v == "1");
+  } else if (k == "lanes") {
+    e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 128 : std::atoi(v.c_str()));
   } else if (k == "large_threshold") {
     e->large_threshold = std::atoi(v.c_str());
   } else if (k == "overlap") {
@@ -1252,6 +1277,18 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "aot_hits") *value = (double)e->aot_hits;
   else if (k == "dtype") *value = e->dtype;
   else if (k == "large_classes") *value = (double)e->large_classes;
+  else if (k == "lane_classes") *value = (double)e->lane_classes;
+  else if (k == "lane_G") *value = e->lane_report.G;
+  else if (k == "lane_R") *value = e->lane_report.R;
+  else if (k == "lane_RA") *value = e->lane_report.RA;
+  else if (k == "lane_nv") *value = e->lane_report.nv;
+  else if (k == "lane_nc_fwd") *value = e->lane_report.nc_fwd;
+  else if (k == "lane_nc_adj") *value = e->lane_report.nc_adj;
+  else if (k == "lane_halo_fwd") *value = e->lane_report.halo_fwd;
+  else if (k == "lane_halo_adj") *value = e->lane_report.halo_adj;
+  else if (k == "lane_halo_p") *value = e->lane_report.halo_p;
+  else if (k == "lane_regs_est") *value = e->lane_report.regs_est;
+  else if (k == "lane_efficiency") *value = e->lane_report.efficiency;
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
@@ -1278,6 +1315,38 @@ int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* need
   if (buf && cap) {
     const size_t n = std::min<size_t>(s.size(), cap - 1);
     std::memcpy(buf, s.data(), n);
+    buf[n] = 0;
+  }
+  PASIF_CATCH(e)
+}
+
+int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t cap, uint64_t* needed) {
+  PASIF_TRY(e)
+  // compiles the run-time specialised kernels of every loaded class for `arch` (e.g. "sm_100a") with ptxas -v and returns
+  // the logs; needs NVRTC but no device (host-only engines included)
+  g_nvrtc.load();
+  std::string out;
+  const std::string a = std::string("--gpu-architecture=") + (arch ? arch : "sm_100a");
+  for (auto* v : {&e->fwd_classes, &e->joint_classes})
+    for (auto& c : *v) {
+      if (c.large) continue;
+      const std::string src = jit_source(c.h, e->dtype);
+      nvrtcProgram prog = nullptr;
+      if (g_nvrtc.CreateProgram(&prog, src.c_str(), "pasif_jit.cu", 0, nullptr, nullptr) != 0) throw std::runtime_error("nvrtcCreateProgram failed");
+      const char* opts[] = {a.c_str(), "-std=c++17", "-lineinfo", "--ptxas-options=-v"};
+      const int rc = g_nvrtc.CompileProgram(prog, 4, opts);
+      size_t n = 0;
+      g_nvrtc.GetProgramLogSize(prog, &n);
+      std::string log(n, '\0');
+      if (n) g_nvrtc.GetProgramLog(prog, &log[0]);
+      while (!log.empty() && log.back() == '\0') log.pop_back();
+      g_nvrtc.DestroyProgram(&prog);
+      out += "== " + c.h.name + " lanes=" + std::to_string(c.h.lanes) + " rc=" + std::to_string(rc) + "\n" + log + "\n";
+    }
+  if (needed) *needed = out.size() + 1;
+  if (buf && cap) {
+    const size_t n = std::min<size_t>(out.size(), cap - 1);
+    std::memcpy(buf, out.data(), n);
     buf[n] = 0;
   }
   PASIF_CATCH(e)

@@ -49,6 +49,11 @@ struct Pattern {
   int N = 0;
   std::vector<int> nv;  // adjoint: needed forward variables (forward-local indices); tensor p-indices refer to this list
   std::vector<int> k_row, k_col, g_o, g_a, g_b, l_o, l_a, l_b, l_c, p_o, p_a, p_b, p_c, p_d, f_row;
+  // lane-block classes (lane_split.hpp): the component is integrated by `lanes` threads; x-operand indices >= N and
+  // p-operand indices >= nv.size() address HALO entries: entry h = published slot pub_slot[hx_pub[h]] (== hx_slot[h]) of
+  // lane (lane + hx_delta[h]) mod lanes; likewise hp_* / ppub_slot over the set-point (nv) list of the adjoint side
+  int lanes = 1;
+  std::vector<int> hx_slot, hx_delta, hx_pub, pub_slot, hp_slot, hp_delta, hp_pub, ppub_slot;
   int nc() const { return (int)(k_row.size() + g_o.size() + l_o.size() + p_o.size() + f_row.size()); }
 
   std::string signature() const {
@@ -64,12 +69,17 @@ struct Pattern {
     put("lo", l_o); put("la", l_a); put("lb", l_b); put("lc", l_c);
     put("po", p_o); put("pa", p_a); put("pb", p_b); put("pc", p_c); put("pd", p_d);
     put("f", f_row);
+    if (lanes > 1) {
+      s << "G" << lanes << ';';
+      put("hxs", hx_slot); put("hxd", hx_delta); put("hps", hp_slot); put("hpd", hp_delta);
+    }
     return s.str();
   }
 };
 
 struct ClassData {
   bool joint = false;
+  int lanes = 1;     // > 1: lane-block class (lane_split.hpp): n_inst counts VIRTUAL instances (instance * lanes + lane)
   Pattern fwd;  // forward pattern (joint: forward part of the joint component)
   Pattern adj;  // joint only
   uint64_t hash = 0;
@@ -386,6 +396,8 @@ inline std::string emit_pattern_struct(const std::string& name, const Pattern& p
   s << "struct " << name << " {\n";
   s << "  static constexpr int N = " << p.N << ", NV = " << p.nv.size() << ", NNZK = " << nk << ", NNZG = " << ng
     << ", NNZL = " << nl << ", NNZP = " << np << ", NF = " << nf << ";\n";
+  s << "  static constexpr int G = " << p.lanes << ", H = " << p.hx_slot.size() << ", NPUB = " << p.pub_slot.size() << ", HP = "
+    << p.hp_slot.size() << ", NPPUB = " << p.ppub_slot.size() << ";\n";
   s << "  static constexpr int OFF_K = 0, OFF_G = " << nk << ", OFF_L = " << nk + ng << ", OFF_P = " << nk + ng + nl
     << ", OFF_F = " << nk + ng + nl + np << ", NC = " << nk + ng + nl + np + nf << ";\n";
   emit_table(s, "nv", p.nv);
@@ -395,6 +407,8 @@ inline std::string emit_pattern_struct(const std::string& name, const Pattern& p
   emit_table(s, "p_o", p.p_o); emit_table(s, "p_a", p.p_a); emit_table(s, "p_b", p.p_b); emit_table(s, "p_c", p.p_c);
   emit_table(s, "p_d", p.p_d);
   emit_table(s, "f_row", p.f_row);
+  emit_table(s, "pub_slot", p.pub_slot); emit_table(s, "hx_pub", p.hx_pub); emit_table(s, "hx_delta", p.hx_delta);
+  emit_table(s, "ppub_slot", p.ppub_slot); emit_table(s, "hp_pub", p.hp_pub); emit_table(s, "hp_delta", p.hp_delta);
   s << "};\n";
   (void)indent;
   return s.str();

@@ -112,11 +112,57 @@ PASIF_DEV void load_vec(const T* src, T (&v)[NV > 0 ? NV : 1]) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ lane-block classes
+// P::G > 1: a component too large for one thread is integrated by a group of G consecutive threads (lane_split.hpp).
+// Every lane owns P::N rows; before each derivative evaluation it publishes the P::NPUB slots other lanes read and
+// fetches its P::H halo operands (slot pub_slot(hx_pub(h)) of lane (lane + hx_delta(h)) mod G) through a
+// double-buffered shared-memory array: one group barrier per exchange.  Thread index p -> lane = p % G,
+// trajectory = p / G = instance * E + e, virtual instance = instance * G + lane.
+template <typename T>
+struct LaneCtx {
+  T* sx;            // [2][NPUB][PASIF_BLOCK]  state / adjoint-state exchange
+  T* sp;            // [2][NPPUB][PASIF_BLOCK] set-point (forward state) exchange of the adjoint kernel
+  int bx, bp;       // current buffer of each
+  int tid, gbase, lane;
+};
+template <int G>
+PASIF_DEV void group_sync() {
+  if constexpr (G <= 32) __syncwarp();
+  else __syncthreads();
+}
+template <typename T, class P, int NXE>
+PASIF_DEV void exchange_x(T (&xe)[NXE], LaneCtx<T>& cx) {
+  if constexpr (P::G > 1 && P::H > 0) {
+    T* b = cx.sx + cx.bx * (P::NPUB * PASIF_BLOCK);
+#pragma unroll
+    for (int k = 0; k < P::NPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = xe[P::pub_slot(k)];
+    group_sync<P::G>();
+#pragma unroll
+    for (int h = 0; h < P::H; ++h)
+      xe[P::N + h] = b[P::hx_pub(h) * PASIF_BLOCK + cx.gbase + ((cx.lane + P::hx_delta(h)) & (P::G - 1))];
+    cx.bx ^= 1;
+  }
+}
+template <typename T, class P, int NPE>
+PASIF_DEV void exchange_p(T (&pe)[NPE], LaneCtx<T>& cx) {
+  if constexpr (P::G > 1 && P::HP > 0) {
+    T* b = cx.sp + cx.bp * (P::NPPUB * PASIF_BLOCK);
+#pragma unroll
+    for (int k = 0; k < P::NPPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = pe[P::ppub_slot(k)];
+    group_sync<P::G>();
+#pragma unroll
+    for (int h = 0; h < P::HP; ++h)
+      pe[P::NV + h] = b[P::hp_pub(h) * PASIF_BLOCK + cx.gbase + ((cx.lane + P::hp_delta(h)) & (P::G - 1))];
+    cx.bp ^= 1;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ derivative
 // y = K x + Gamma:(x,p) + Lambda:(x,p,p) + Psi:(x,p,p,p) + F fe        (forward: p == x)
+// x / p may be longer than the row count: lane-block classes append the halo entries (operands owned by other lanes)
 template <typename T, class P, int NX, int NP_>
 PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::NC > 0 ? P::NC : 1], T fe,
-                          T (&y)[NX]) {
+                          T (&y)[P::N]) {
 #pragma unroll
   for (int r = 0; r < P::N; ++r) y[r] = T(0);
 #pragma unroll
@@ -136,18 +182,26 @@ PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::N
 
 // one classical RK4 step of the forward system; fa/fb/fc = force sample of stage 1 / stages 2,3 / stage 4
 template <typename T, class P>
-PASIF_DEV void rk4_forward_step(T (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1], T fa, T fb, T fc, T h, T h2, T h6) {
-  T m[P::N], s[P::N], mi[P::N];
-  derivative<T, P, P::N, P::N>(q, q, c, fa, m);
+PASIF_DEV void rk4_forward_step(T (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1], T fa, T fb, T fc, T h, T h2, T h6,
+                                LaneCtx<T>& cx) {
+  constexpr int NXE = P::N + P::H;
+  T m[P::N], s[P::N], mi[NXE];
+#pragma unroll
+  for (int i = 0; i < P::N; ++i) mi[i] = q[i];
+  exchange_x<T, P, NXE>(mi, cx);
+  derivative<T, P, NXE, NXE>(mi, mi, c, fa, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = m[i]; mi[i] = fma(h2, m[i], q[i]); }
-  derivative<T, P, P::N, P::N>(mi, mi, c, fb, m);
+  exchange_x<T, P, NXE>(mi, cx);
+  derivative<T, P, NXE, NXE>(mi, mi, c, fb, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h2, m[i], q[i]); }
-  derivative<T, P, P::N, P::N>(mi, mi, c, fb, m);
+  exchange_x<T, P, NXE>(mi, cx);
+  derivative<T, P, NXE, NXE>(mi, mi, c, fb, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h, m[i], q[i]); }
-  derivative<T, P, P::N, P::N>(mi, mi, c, fc, m);
+  exchange_x<T, P, NXE>(mi, cx);
+  derivative<T, P, NXE, NXE>(mi, mi, c, fc, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) q[i] = fma(h6, s[i] + m[i], q[i]);
 }
@@ -157,11 +211,17 @@ PASIF_DEV void rk4_forward_step(T (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1
 template <typename T, class PF, class DV>
 PASIF_DEV void forward_body(const FwdArgs<T>& a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
-  if (p >= a.n_traj) return;
-  const int inst = p / a.E;
-  const int e = p - inst * a.E;
+  if (p >= a.n_traj) return;                       // lane-block classes: whole groups leave together (n_traj % G == 0)
+  constexpr int G = PF::G;
+  const int lane = p & (G - 1);
+  const int traj = p / G;
+  const int e = traj % a.E;
+  const int inst = (traj / a.E) * G + lane;       // virtual instance (G == 1: the instance itself)
   constexpr int N = PF::N;
   constexpr int NC = PF::NC > 0 ? PF::NC : 1;
+  constexpr int SXN = (G > 1 && PF::H > 0) ? 2 * PF::NPUB * PASIF_BLOCK : 1;
+  __shared__ T sm_x[SXN];
+  LaneCtx<T> cx{sm_x, nullptr, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
 
   T c[NC];
 #pragma unroll
@@ -206,7 +266,10 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
         } else {
           T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
 #pragma unroll
-          for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+          for (int i = 0; i < N; ++i) {
+            const int g = a.varmap[(long long)i * a.n_inst + inst];
+            if (G == 1 || g >= 0) dst[g] = q[i];                                 // -1: padding slot of a lane
+          }
         }
       }
       ++save_slot;
@@ -225,16 +288,16 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
     for (; t + 4 <= a.t1; t += 4) {
       const T n0 = ex[0], n1 = ex[E], n2 = ex[2 * E], n3 = ex[3 * E];           // e[t+5 .. t+8]
       ex += 4 * E;
-      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6); after_step();
-      rk4_forward_step<T, PF>(q, c, e1, e1, e2, h, h2, h6); after_step();
-      rk4_forward_step<T, PF>(q, c, e2, e2, e3, h, h2, h6); after_step();
-      rk4_forward_step<T, PF>(q, c, e3, e3, e4, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
+      rk4_forward_step<T, PF>(q, c, e1, e1, e2, h, h2, h6, cx); after_step();
+      rk4_forward_step<T, PF>(q, c, e2, e2, e3, h, h2, h6, cx); after_step();
+      rk4_forward_step<T, PF>(q, c, e3, e3, e4, h, h2, h6, cx); after_step();
       e0 = e4; e1 = n0; e2 = n1; e3 = n2; e4 = n3;
     }
     for (; t < a.t1; ++t) {
       const T n0 = *ex;
       ex += E;
-      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
       e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = n0;
     }
   } else {
@@ -246,7 +309,7 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
     for (int t = a.t0; t < a.t1; ++t) {
       const T g1 = ex[0], g2 = ex[E];                                            // f[2t+3], f[2t+4]
       ex += 2 * E;
-      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6); after_step();
+      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6, cx); after_step();
       f0 = f2; f1 = g1; f2 = g2;
     }
   }
@@ -258,7 +321,10 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
   if (a.final_user) {
     T* dst = a.final_user + (long long)e * a.n_glob;
 #pragma unroll
-    for (int i = 0; i < N; ++i) dst[a.varmap[(long long)i * a.n_inst + inst]] = q[i];
+    for (int i = 0; i < N; ++i) {
+      const int g = a.varmap[(long long)i * a.n_inst + inst];
+      if (G == 1 || g >= 0) dst[g] = q[i];
+    }
   }
 }
 
@@ -270,10 +336,19 @@ template <typename T, class PA>
 PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   const int p = blockIdx.x * blockDim.x + threadIdx.x;
   if (p >= a.n_traj) return;
-  const int inst = p / a.E;
+  constexpr int G = PA::G;
+  const int lane = p & (G - 1);
+  const int inst = (p / G / a.E) * G + lane;       // virtual instance (G == 1: the instance itself)
   constexpr int N = PA::N;
   constexpr int NC = PA::NC > 0 ? PA::NC : 1;
   constexpr int NV = PA::NV > 0 ? PA::NV : 1;
+  constexpr int NXE = N + PA::H;                   // adjoint state + halo
+  constexpr int NPE = NV + PA::HP;                 // needed forward variables + halo
+  constexpr int SXN = (G > 1 && PA::H > 0) ? 2 * PA::NPUB * PASIF_BLOCK : 1;
+  constexpr int SPN = (G > 1 && PA::HP > 0) ? 2 * PA::NPPUB * PASIF_BLOCK : 1;
+  __shared__ T sm_x[SXN];
+  __shared__ T sm_p[SPN];
+  LaneCtx<T> cx{sm_x, sm_p, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
 
   T c[NC];
 #pragma unroll
@@ -285,8 +360,9 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   const T h = a.h, h2 = a.h2, h6 = a.h6;
   const long long stride = (long long)PA::NV * a.n_traj;
   const T* d = a.dense + (long long)p * PA::NV + (long long)(a.len - 1) * stride;    // state index i = len-1
-  T qa[NV], qn[NV], qh[NV];
-  load_vec<T, PA::NV>(d, qa);
+  T qa[NPE], qn[NV], qh[NPE];
+  load_vec<T, PA::NV>(d, reinterpret_cast<T(&)[NV]>(qa));
+  exchange_p<T, PA, NPE>(qa, cx);
   // software prefetch: qn = state i-1 of the CURRENT iteration, loaded one iteration ahead
   if (a.len >= 2) load_vec<T, PA::NV>(d - stride, qn);
   else {
@@ -297,10 +373,11 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   for (int i = a.len - 1; i >= 0; --i) {
     // qb = forward state of index i-1.  Literal-reference mode: when i-1 is the aliased scratch slot the reference
     // reads back what it has just written there, i.e. the current qa.
-    T qb[NV];
+    T qb[NPE];
     const bool aliased = (i - 1 == a.alias_local);
 #pragma unroll
     for (int v = 0; v < PA::NV; ++v) qb[v] = aliased ? qa[v] : qn[v];
+    exchange_p<T, PA, NPE>(qb, cx);
     // prefetch state i-2 for the next iteration
     if (i >= 2) load_vec<T, PA::NV>(d - 2 * stride, qn);
     else if (i == 1) {
@@ -309,23 +386,29 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
     }
     d -= stride;
 #pragma unroll
-    for (int v = 0; v < PA::NV; ++v) qh[v] = T(.5) * (qa[v] + qb[v]);
+    for (int v = 0; v < PA::NV + PA::HP; ++v) qh[v] = T(.5) * (qa[v] + qb[v]);
 
-    T m[N], s[N], mi[N];
-    derivative<T, PA, N, NV>(lam, qa, c, T(0), m);
+    T m[N], s[N], mi[NXE];
+#pragma unroll
+    for (int k = 0; k < N; ++k) mi[k] = lam[k];
+    exchange_x<T, PA, NXE>(mi, cx);
+    derivative<T, PA, NXE, NPE>(mi, qa, c, T(0), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = m[k]; mi[k] = fma(h2, m[k], lam[k]); }
-    derivative<T, PA, N, NV>(mi, qh, c, T(0), m);
+    exchange_x<T, PA, NXE>(mi, cx);
+    derivative<T, PA, NXE, NPE>(mi, qh, c, T(0), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h2, m[k], lam[k]); }
-    derivative<T, PA, N, NV>(mi, qh, c, T(0), m);
+    exchange_x<T, PA, NXE>(mi, cx);
+    derivative<T, PA, NXE, NPE>(mi, qh, c, T(0), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h, m[k], lam[k]); }
-    derivative<T, PA, N, NV>(mi, qb, c, T(0), m);
+    exchange_x<T, PA, NXE>(mi, cx);
+    derivative<T, PA, NXE, NPE>(mi, qb, c, T(0), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) lam[k] = fma(h6, s[k] + m[k], lam[k]);
 #pragma unroll
-    for (int v = 0; v < PA::NV; ++v) qa[v] = qb[v];
+    for (int v = 0; v < PA::NV + PA::HP; ++v) qa[v] = qb[v];
   }
 
 #pragma unroll
@@ -333,7 +416,7 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
 }
 
 struct NoDense {
-  static constexpr int NV = 0;
+  static constexpr int NV = 0, G = 1, H = 0, HP = 0, NPUB = 0, NPPUB = 0;
   PASIF_DEV static constexpr int nv(int) { return 0; }
 };
 

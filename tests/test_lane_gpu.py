@@ -1,0 +1,78 @@
+"""GPU suite for the LANE-BLOCK path (pasif_b200/csrc/lane_split.hpp + the lane-aware register kernels in
+rk4_kernels.cuh): a component too large for one thread is integrated by a group of G threads, every lane keeping its
+share of the state in registers and exchanging a few halo operands per RK4 stage.  Called through the C ABI and compared
+with the C oracle (the restated reference algorithm) and with the tile kernels on the same inputs:
+  * sparse oscillator chains (BASELINE config 4 shape, scaled down), forward + trajectory + adjoint, both schedules, both
+    precisions, several group widths (lanes = 8 .. 128, one warp and several warps per trajectory);
+  * several instances with their own coefficients; an excitation count that leaves the last CTA partly filled;
+  * the reference's golden vectors with every component forced through the split (whatever the cost model then keeps).
+Tolerances as in test_parity_gpu.py (fp64 <= 1e-12 per variable; fp32 <= 1e-5 forward / 5e-5 adjoint on the vector)."""
+import numpy as np
+import pytest
+
+from conftest import golden, rel_err, col_err, run_case
+from pasif_b200 import capi, workloads as wl
+from test_large_gpu import TOL_ADJ, TOL_FWD, _oracle, chain_case, close
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("compat", ["reference", "clean"])
+@pytest.mark.parametrize("ndof,lanes", [(40, "on"), (40, "16"), (100, "on"), (150, "128")])
+def test_chain_through_lane_groups_matches_oracle(ndof, lanes, compat, prec):
+    case = chain_case(ndof, False, E=11, L=700)
+    a = run_case(capi.engine_class(prec, compat), case, options={"lanes": lanes})
+    b = run_case(_oracle(prec, compat), case)
+    p = a["_p"]
+    assert p._query("lane_classes") >= 2 and p._query("large_classes") == 0      # forward class + joint class
+    assert p._query("lane_G") <= (128 if lanes == "on" else int(lanes))
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert np.array_equal(a["amplitudes"], a["amplitudes_2nd"])
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lane_groups_agree_with_tile_kernels(prec):
+    """same inputs through the lane-block split and through the shared-memory tile kernels"""
+    case = chain_case(60, False, E=37, L=400)
+    a = run_case(capi.engine_class(prec), case)
+    t = run_case(capi.engine_class(prec), case, options={"lanes": "off"})
+    assert a["_p"]._query("lane_classes") >= 2 and t["_p"]._query("lane_classes") == 0
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], t["amplitudes"], n, prec, TOL_FWD)
+    assert close(a["gradient"], t["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_several_chain_instances_through_lane_groups(prec):
+    case = chain_case(30, False, E=19, L=500, n_sys=3)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("lane_classes") >= 2
+    n = sum(s["n"] for s in case["systems"])
+    na = sum(s["n"] for s in case["jacobians"])
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+    red = np.asarray(a["_p"]._getGradientReduced(0))
+    assert rel_err(red, a["gradient"].reshape(19, na).sum(axis=0)) < (1e-12 if prec == "f64" else 1e-5)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("name", ["mixed2", "fit8x2_jit", "ex1dof_short", "ex1dof_interp", "fit8_e16"])
+def test_golden_with_every_component_offered_to_the_split(name, prec):
+    """large_threshold = 0 offers every component to the lane-block split; the cost model keeps it or hands the component
+    to the tile kernels -- either way the reference's golden vectors must be reproduced."""
+    z = golden(name, prec)
+    case = wl.golden_case(name)
+    out = run_case(capi.engine_class(prec), case, options={"large_threshold": "0"})
+    p = out["_p"]
+    assert p._query("lane_classes") + p._query("large_classes") >= 1
+    E = len(case["excitations"])
+    assert close(out["amplitudes"], z["amplitudes"], z["amplitudes"].size // E, prec, TOL_FWD)
+    if "trajectory" in z.files:
+        assert rel_err(out["trajectory"][1:], z["trajectory"][1:]) < TOL_FWD[prec]
+    if "gradient" in z.files:
+        assert close(out["gradient"], z["gradient"], z["gradient"].size // E, prec, TOL_ADJ)

@@ -16,7 +16,7 @@ pytestmark = pytest.mark.gpu
 
 TOL_FWD = {"f64": 1e-12, "f32": 1e-5}
 TOL_ADJ = {"f64": 1e-12, "f32": 5e-5}
-FORCE_LARGE = {"large_threshold": "0"}
+FORCE_LARGE = {"large_threshold": "0", "lanes": "off"}
 
 
 def _oracle(prec, compat):
@@ -62,13 +62,14 @@ def chain_case(ndof, dense, E, L, n_sys=1, seed=3):
 @pytest.mark.parametrize("compat", ["reference", "clean"])
 @pytest.mark.parametrize("mode", ["sparse", "dense-stage", "dense-tile"])
 def test_chain_matches_oracle(mode, compat, prec):
-    """sparse: row programs in the tile kernels; dense-stage: per-stage batched GEMM + fused update with the state in
-    HBM (the default for a dense shared K'); dense-tile: GEMM inside the tile kernels."""
+    """sparse: row programs in the tile kernels (lane-block split switched off); dense-stage: per-stage batched GEMM +
+    fused update with the state in HBM (the default for a dense shared K'); dense-tile: GEMM inside the tile kernels."""
     dense = mode != "sparse"
     case = chain_case(40, dense, E=11, L=700)
-    a = run_case(capi.engine_class(prec, compat), case, options={"gemm": "tile"} if mode == "dense-tile" else None)
+    a = run_case(capi.engine_class(prec, compat), case, options={"gemm": "tile"} if mode == "dense-tile" else ({"lanes": "off"} if mode == "sparse" else None))
     b = run_case(_oracle(prec, compat), case)
     assert a["_p"]._query("large_classes") >= 1
+    assert a["_p"]._query("lane_classes") == 0
     assert (a["_p"]._query("large_stage_classes") >= 1) == (mode == "dense-stage")
     assert (a["_p"]._query("large_gemm_classes") >= 1) == dense
     n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
@@ -80,7 +81,7 @@ def test_chain_matches_oracle(mode, compat, prec):
 def test_gemm_path_is_used_and_agrees_with_row_programs():
     """Dense shared K': the tensor-core path (DMMA) and the sparse row programs (gemm=off) give the same fp64 result."""
     case = chain_case(48, True, E=16, L=400)
-    b = run_case(capi.engine_class("f64"), case, options={"gemm": "off"})
+    b = run_case(capi.engine_class("f64"), case, options={"gemm": "off", "lanes": "off"})
     assert b["_p"]._query("large_gemm_classes") == 0
     n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
     for mode in ("stage", "tile"):
@@ -94,7 +95,7 @@ def test_gemm_path_is_used_and_agrees_with_row_programs():
 @pytest.mark.parametrize("prec", ["f64", "f32"])
 def test_several_chain_instances_ragged_tiles(prec):
     case = chain_case(30, False, E=19, L=500, n_sys=3)
-    a = run_case(capi.engine_class(prec), case)
+    a = run_case(capi.engine_class(prec), case, options={"lanes": "off"})
     b = run_case(_oracle(prec, "reference"), case)
     n = sum(s["n"] for s in case["systems"])
     na = sum(s["n"] for s in case["jacobians"])
