@@ -241,6 +241,7 @@ def main():
                     help="adjoint schedule: the reference's literal one (default, parity with its outputs) or the exact "
                          "discrete adjoint, whose chunk trajectories are kept from the forward sweep as far as HBM allows")
     ap.add_argument("--tail-budget-gb", default="auto", help="clean schedule: device memory for kept chunk trajectories")
+    ap.add_argument("--lane-regs", default="", help="register estimate up to which a lane pattern is accepted (debug)")
     ap.add_argument("--lanes", default="on", help="lane-block split of large components: on | off | widest group (8..128)")
     a = ap.parse_args()
     w = dict(WORKLOADS[a.workload])
@@ -295,6 +296,8 @@ def main():
     p._setOption("compat", a.compat)
     p._setOption("tail_budget_gb", a.tail_budget_gb)
     p._setOption("lanes", a.lanes)
+    if a.lane_regs:
+        p._setOption("lane_regs", a.lane_regs)
     t_setup = time.time()
     p.setSystems(*wl.to_frontend_args(systems, mod))
     p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))

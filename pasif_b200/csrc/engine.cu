@@ -398,6 +398,7 @@ struct pasif_engine {
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
   int lanes_max = 128;                           // widest thread group of the lane-block split (0: off)
+  int lane_regs = 240;                           // register estimate a lane pattern may reach before a wider group is tried
   long long lane_classes = 0;
   LaneSplitReport lane_report;                   // of the last class that was split
   std::string lane_reject;                       // why the last large class was not split
@@ -603,7 +604,7 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
       // (dense operators, irregular coupling) stay with the tile kernels / the dense-operator path below
       ClassData split;
       LaneSplitReport rep;
-      if (lane_split(dc.h, (int)sizeof(T), E.lanes_max, split, rep)) {
+      if (lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, split, rep)) {
         dc.h = std::move(split);
         ++E.lane_classes;
         E.lane_report = rep;
@@ -1198,6 +1199,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
     e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 128 : std::atoi(v.c_str()));
+  } else if (k == "lane_regs") {
+    e->lane_regs = std::atoi(v.c_str());
   } else if (k == "large_threshold") {
     e->large_threshold = std::atoi(v.c_str());
   } else if (k == "overlap") {

@@ -287,6 +287,41 @@ inline void match_units(const Graph& g, std::vector<int>& unit_of, std::vector<s
   }
 }
 
+// Observer units -- units no row outside them reads (probe variables such as p1' = x_0^2, p2' = p1) -- do not belong on the
+// line of units: each is absorbed as extra members into the unit it reads most from, so that it costs a few extra slots
+// instead of a whole position on every lane.
+inline void absorb_observers(const Pattern& f, const Graph& g, std::vector<int>& unit_of, std::vector<std::vector<int>>& units) {
+  for (bool changed = true; changed;) {
+    changed = false;
+    const int nu = (int)units.size();
+    std::vector<char> feeds((size_t)nu, 0);
+    auto use = [&](int out, int operand) { if (unit_of[(size_t)out] != unit_of[(size_t)operand]) feeds[(size_t)unit_of[(size_t)operand]] = 1; };
+    for (size_t k = 0; k < f.k_row.size(); ++k) use(f.k_row[k], f.k_col[k]);
+    for (size_t k = 0; k < f.g_o.size(); ++k) { use(f.g_o[k], f.g_a[k]); use(f.g_o[k], f.g_b[k]); }
+    for (size_t k = 0; k < f.l_o.size(); ++k) { use(f.l_o[k], f.l_a[k]); use(f.l_o[k], f.l_b[k]); use(f.l_o[k], f.l_c[k]); }
+    for (size_t k = 0; k < f.p_o.size(); ++k) { use(f.p_o[k], f.p_a[k]); use(f.p_o[k], f.p_b[k]); use(f.p_o[k], f.p_c[k]); use(f.p_o[k], f.p_d[k]); }
+    for (int u = 0; u < nu && !changed; ++u) {
+      if (feeds[(size_t)u] || units[(size_t)u].empty()) continue;
+      std::map<int, int> w;
+      for (int v : units[(size_t)u])
+        for (auto& kv : g[(size_t)v])
+          if (unit_of[(size_t)kv.first] != u) w[unit_of[(size_t)kv.first]] += kv.second;
+      int best = -1, bw = 0;
+      for (auto& kv : w) if (kv.second > bw) { best = kv.first; bw = kv.second; }
+      if (best < 0) continue;
+      for (int v : units[(size_t)u]) { units[(size_t)best].push_back(v); unit_of[(size_t)v] = best; }
+      units[(size_t)u].clear();
+      changed = true;
+    }
+    if (changed) {   // compact
+      std::vector<std::vector<int>> nu2;
+      for (auto& m : units) if (!m.empty()) nu2.push_back(m);
+      units.swap(nu2);
+      for (size_t u = 0; u < units.size(); ++u) for (int v : units[u]) unit_of[(size_t)v] = (int)u;
+    }
+  }
+}
+
 // Cuthill-McKee order of the unit graph from a pseudo-peripheral unit
 inline std::vector<int> cm_order(const Graph& g, const std::vector<int>& unit_of, int n_units) {
   std::vector<std::set<int>> ug((size_t)n_units);
@@ -345,6 +380,7 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   std::vector<int> unit_of;
   std::vector<std::vector<int>> units;
   match_units(g, unit_of, units);
+  absorb_observers(F, g, unit_of, units);
   const int n_units = (int)units.size();
   std::vector<int> order;
   if (cm) order = cm_order(g, unit_of, n_units);
@@ -532,11 +568,10 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
 
 // Tries group widths from narrow to wide and both unit orders; keeps the first width that fits the register budget,
 // with the order that gives the smaller common pattern.
-inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, ClassData& out, LaneSplitReport& rep) {
+inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, ClassData& out, LaneSplitReport& rep) {
   const long long terms = (long long)c.fwd.nc() + c.adj.nc();
   const long long rows = (long long)c.fwd.N + c.adj.N;
   if (terms > 64 * rows) { rep.why = "operator too dense for a lane split (" + std::to_string(terms / std::max<long long>(rows, 1)) + " terms per row)"; return false; }
-  const int reg_budget = 224;
   const double min_eff = 0.30;
   for (int G = 8; G <= max_lanes; G *= 2) {
     ClassData best;

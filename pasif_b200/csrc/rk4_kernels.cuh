@@ -126,9 +126,10 @@ struct LaneCtx {
   int tid, gbase, lane;
 };
 template <int G>
-PASIF_DEV void group_sync() {
+PASIF_DEV void group_sync(int tid) {
   if constexpr (G <= 32) __syncwarp();
-  else __syncthreads();
+  else if constexpr (G >= PASIF_BLOCK) __syncthreads();
+  else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / G), "n"(G) : "memory");   // one named barrier per group of the CTA
 }
 template <typename T, class P, int NXE>
 PASIF_DEV void exchange_x(T (&xe)[NXE], LaneCtx<T>& cx) {
@@ -136,7 +137,7 @@ PASIF_DEV void exchange_x(T (&xe)[NXE], LaneCtx<T>& cx) {
     T* b = cx.sx + cx.bx * (P::NPUB * PASIF_BLOCK);
 #pragma unroll
     for (int k = 0; k < P::NPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = xe[P::pub_slot(k)];
-    group_sync<P::G>();
+    group_sync<P::G>(cx.tid);
 #pragma unroll
     for (int h = 0; h < P::H; ++h)
       xe[P::N + h] = b[P::hx_pub(h) * PASIF_BLOCK + cx.gbase + ((cx.lane + P::hx_delta(h)) & (P::G - 1))];
@@ -149,7 +150,7 @@ PASIF_DEV void exchange_p(T (&pe)[NPE], LaneCtx<T>& cx) {
     T* b = cx.sp + cx.bp * (P::NPPUB * PASIF_BLOCK);
 #pragma unroll
     for (int k = 0; k < P::NPPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = pe[P::ppub_slot(k)];
-    group_sync<P::G>();
+    group_sync<P::G>(cx.tid);
 #pragma unroll
     for (int h = 0; h < P::HP; ++h)
       pe[P::NV + h] = b[P::hp_pub(h) * PASIF_BLOCK + cx.gbase + ((cx.lane + P::hp_delta(h)) & (P::G - 1))];
