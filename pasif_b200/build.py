@@ -36,7 +36,7 @@ def _run(cmd):
 
 
 def build_library(force=False, verbose=False):
-    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "rk4_kernels.cuh", "large_kernels.cuh", "large_host.inc", "stage_kernels.cuh", "stage_tcgen05.cuh", "stage_host.inc", "pattern.hpp", "patterns_aot.inc")] + \
+    srcs = [os.path.join(CSRC, f) for f in ("engine.cu", "rk4_kernels.cuh", "large_kernels.cuh", "large_host.inc", "stage_kernels.cuh", "stage_tcgen05.cuh", "stage_host.inc", "pattern.hpp", "lane_split.hpp", "patterns_aot.inc")] + \
            [os.path.join(os.path.dirname(HERE), "include", "pasif_b200.h")]
     if not force and _newer(LIB, srcs):
         return LIB

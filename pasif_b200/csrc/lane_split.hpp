@@ -490,6 +490,12 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   if (rep.regs_est > reg_budget) { rep.why = "register estimate " + std::to_string(rep.regs_est) + " > " + std::to_string(reg_budget); return false; }
   if (rep.efficiency < min_eff) { rep.why = "only " + std::to_string((int)(rep.efficiency * 100)) + " % of the common pattern's terms are real"; return false; }
   if (fa.R > 48 || (c.joint && aa.R > 48)) { rep.why = "more than 48 slots per lane"; return false; }
+  // a lane that reads more operands from other lanes than it owns is a dense coupling: the exchange would dominate, and
+  // the dense-operator path (tensor-core GEMM per stage) is the one built for it
+  if (rep.halo_fwd > std::max(24, 2 * fa.R) || (c.joint && rep.halo_adj + rep.halo_p > std::max(24, 2 * aa.R))) {
+    rep.why = "too many halo operands per lane (dense coupling)";
+    return false;
+  }
 
   // ---- tables of the virtual instances
   out = ClassData();

@@ -162,6 +162,44 @@ def chain_system(ndof, dense=False, seed=3, k=2.0e4, b=8.0, g=40.0, lam=3.0e5, F
     return _sys(N, M, (bv, br, bc), (kv, kr, kc), ([N] * 3, gval, gidx), ([N] * 4, lval, lidx), F, np.zeros(N))
 
 
+def lattice_system(nx, ny, seed=5, k=2.0e4, b=8.0, g=40.0, lam=3.0e5, F0=2.0e4):
+    """nx x ny membrane of unit masses: nearest-neighbour springs in both directions (fixed rim), diagonal damping, on-site
+    quadratic and cubic terms, same probe pair as `chain_system`.  State [x (site-major, i * ny + j), v, p2, p1].  A second
+    large-component shape for the lane-block split: couplings reach +-1 and +-ny sites."""
+    rng = np.random.default_rng(seed)
+    n = int(nx) * int(ny)
+    N = 2 * n + 2
+    p2, p1 = 2 * n, 2 * n + 1
+    M = np.ones(N)
+    M[n:2 * n] = rng.uniform(0.8, 1.25, size=n)
+    bv, br, bc = [-1.0] * n + [-1.0], list(range(n)) + [p2], list(range(n, 2 * n)) + [p1]
+    kv, kr, kc = [], [], []
+    kx = k * rng.uniform(0.8, 1.25, size=(nx + 1, ny))          # spring between (i-1, j) and (i, j); rows 0 / nx: the rim
+    ky = k * rng.uniform(0.8, 1.25, size=(nx, ny + 1))
+    for i in range(nx):
+        for j in range(ny):
+            s_ = i * ny + j
+            kv.append(kx[i, j] + kx[i + 1, j] + ky[i, j] + ky[i, j + 1]); kr.append(n + s_); kc.append(s_)
+            if i > 0:
+                kv.append(-kx[i, j]); kr.append(n + s_); kc.append(s_ - ny)
+            if i < nx - 1:
+                kv.append(-kx[i + 1, j]); kr.append(n + s_); kc.append(s_ + ny)
+            if j > 0:
+                kv.append(-ky[i, j]); kr.append(n + s_); kc.append(s_ - 1)
+            if j < ny - 1:
+                kv.append(-ky[i, j + 1]); kr.append(n + s_); kc.append(s_ + 1)
+    for s_ in range(n):
+        bv.append(b * rng.uniform(0.8, 1.25)); br.append(n + s_); bc.append(n + s_)
+    gval, gidx = [-1.0], [p1, 0, 0]
+    lval, lidx = [], []
+    for s_ in range(n):
+        gval.append(g * rng.uniform(0.5, 1.5)); gidx += [n + s_, s_, s_]
+        lval.append(lam * rng.uniform(0.5, 1.5)); lidx += [n + s_, s_, s_, s_]
+    F = np.zeros(N)
+    F[n:2 * n] = F0 * rng.uniform(0.2, 1.0, size=n)
+    return _sys(N, M, (bv, br, bc), (kv, kr, kc), ([N] * 3, gval, gidx), ([N] * 4, lval, lidx), F, np.zeros(N))
+
+
 def chain_jacobian(system, n_params=4):
     """Adjoint system of `chain_system` for the loss p1(T) = int x_0^2 dt with gradients w.r.t. the first `n_params`
     on-site cubic coefficients (pasif_b200.adjoint.build_adjoint)."""

@@ -76,3 +76,24 @@ def test_golden_with_every_component_offered_to_the_split(name, prec):
         assert rel_err(out["trajectory"][1:], z["trajectory"][1:]) < TOL_FWD[prec]
     if "gradient" in z.files:
         assert close(out["gradient"], z["gradient"], z["gradient"].size // E, prec, TOL_ADJ)
+
+
+def lattice_case(nx, ny, E, L):
+    s = wl.lattice_system(nx, ny)
+    return dict(systems=[s], jacobians=[wl.chain_jacobian(s, 3)], excitations=wl.random_sine_excitations(E, L, 16000, seed=9),
+                sample_rate=16000, numsteps=0, interp=None, traj_save_steps=max(L // 5, 1))
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("shape", [(8, 8), (6, 10), (16, 16)])
+def test_membrane_through_lane_groups_matches_oracle(shape, prec):
+    """2-D lattice of oscillators: couplings reach +-1 and +-ny sites, so a lane exchanges a whole row of halo operands"""
+    case = lattice_case(*shape, E=7, L=300)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    p = a["_p"]
+    assert p._query("lane_classes") >= 2 and p._query("lane_halo_fwd") >= 6
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
