@@ -241,6 +241,7 @@ def main():
                     help="adjoint schedule: the reference's literal one (default, parity with its outputs) or the exact "
                          "discrete adjoint, whose chunk trajectories are kept from the forward sweep as far as HBM allows")
     ap.add_argument("--tail-budget-gb", default="auto", help="clean schedule: device memory for kept chunk trajectories")
+    ap.add_argument("--stage-parts", default="", help="dense-operator path: number of batch parts on their own streams (debug)")
     ap.add_argument("--lane-regs", default="", help="register estimate up to which a lane pattern is accepted (debug)")
     ap.add_argument("--lanes", default="on", help="lane-block split of large components: on | off | widest group (8..128)")
     a = ap.parse_args()
@@ -298,6 +299,8 @@ def main():
     p._setOption("lanes", a.lanes)
     if a.lane_regs:
         p._setOption("lane_regs", a.lane_regs)
+    if a.stage_parts:
+        p._setOption("stage_parts", a.stage_parts)
     t_setup = time.time()
     p.setSystems(*wl.to_frontend_args(systems, mod))
     p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
@@ -432,7 +435,9 @@ def main():
         pad = lambda n, m: (n + m - 1) // m * m
         mult = 3 if w["dtype"] == "f32" else 1
         ppad = pad(pairs, 128)
-        gemm_flops = {"gfwd": 2.0 * pad(N_FWD, 32) ** 2 * ppad * mult, "bwd": 2.0 * pad(N_ADJ, 32) ** 2 * ppad * mult}
+        # the GEMM covers the band of dense rows of K' (x' = v rows and probes stay row programs): rows x padded columns
+        gemm_flops = {"gfwd": 2.0 * p._query("stage_band_rows_fwd") * pad(N_FWD, 32) * ppad * mult,
+                      "bwd": 2.0 * p._query("stage_band_rows_adj") * pad(N_ADJ, 32) * ppad * mult}
         if w["dtype"] == "f32":
             tpeak = peaks.get("bf16_tflops", 1590.0) / 2.0
             tsrc = "tf32 dense = half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2" if peaks else "fallback 1590 / 2"
@@ -445,6 +450,7 @@ def main():
         tensor = {"bound": "tensor", "kernel": tname, "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
                   "traffic": None, "peak_source": tsrc, "tensor_products_per_useful_product": mult,
                   "useful_tflops": ach / mult, "gemm_us_per_launch": per_kernel[dom]["avg_launch_ms"] * 1e3,
+                  "gemm_rows": {"fwd": p._query("stage_band_rows_fwd"), "adj": p._query("stage_band_rows_adj")},
                   "gemm_share_of_step": (k_ms["gfwd"] + k_ms["bwd"]) / max(serial_ms, 1e-9),
                   "whole_step": {"achieved": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12,
                                  "frac": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12 / (tpeak / mult)},

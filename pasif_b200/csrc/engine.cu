@@ -393,6 +393,11 @@ struct pasif_engine {
   cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: adjoint sweep of chunk k overlaps the recompute of chunk k-1
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
   cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
+  // dense-operator path: the batch is cut into `stage_nparts` parts, each with its own stream, so that the tensor-bound
+  // GEMM of one part overlaps the HBM-bound update of another (part 0 runs on `stream`)
+  int stage_nparts = 4;
+  std::vector<cudaStream_t> part_streams;
+  std::vector<cudaEvent_t> part_events;
   bool overlap = true;
   std::string err;
   bool compat_clean = false, jit_on = true, gemm_on = true;
@@ -404,6 +409,7 @@ struct pasif_engine {
   std::string lane_reject;                       // why the last large class was not split
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
+  bool gemm_band = true;                         // dense-operator path: only the band of dense rows goes through the GEMM
   bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
   int block = PASIF_BLOCK, n_sm = 148;
   double last_ms = 0;
@@ -1093,6 +1099,8 @@ void pasif_destroy(pasif_engine* e) {
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
     }
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    for (cudaStream_t st : e->part_streams) cudaStreamDestroy(st);
+    for (cudaEvent_t ev : e->part_events) cudaEventDestroy(ev);
     if (e->stream) cudaStreamSynchronize(e->stream);
     e->h_stage.release();
     for (int i = 0; i < 2; ++i) if (e->ev_stage[i]) cudaEventDestroy(e->ev_stage[i]);
@@ -1195,6 +1203,12 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     // "on" / "stage": per-stage batched GEMM (stage_kernels.cuh); "tile": GEMM inside the tile kernels; "off": row programs
     e->gemm_on = (v == "on" || v == "1" || v == "stage" || v == "tile");
     e->gemm_stage = (v != "tile");
+  } else if (k == "stage_parts") {
+    const int n = std::atoi(v.c_str());
+    if (n < 1 || n > 16) throw std::runtime_error("stage_parts must be in [1, 16]");
+    e->stage_nparts = n;
+  } else if (k == "gemm_band") {
+    e->gemm_band = (v == "on" || v == "1");
   } else if (k == "tcgen05") {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
@@ -1295,6 +1309,16 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
+  else if (k == "stage_band_rows_fwd" || k == "stage_band_rows_adj") {
+    // rows of K' that go through the per-stage GEMM of the (first) dense-operator class
+    *value = 0;
+    for (auto* v : {&e->joint_classes, &e->fwd_classes})
+      for (auto& c : *v)
+        if (*value == 0 && c.large && c.large->stage) {
+          const LargeSide& sd = k == "stage_band_rows_fwd" ? c.large->fwd : c.large->adj;
+          *value = (double)(sd.band_hi - sd.band_lo);
+        }
+  }
   else if (k == "aot_table_size") *value = (double)aot_table().size();
   else if (k == "ms_fwd") *value = e->kind_ms[0];
   else if (k == "ms_gfwd") *value = e->kind_ms[1];

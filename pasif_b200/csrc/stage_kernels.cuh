@@ -24,7 +24,8 @@ using pasif_large::Tables;
 // ------------------------------------------------------------------------------------------------ fused stage update
 template <typename T>
 struct UpdArgs {
-  Tables tb;             // row programs without K (WK = 0); NPR = row stride of the set-point arrays
+  Tables tb;             // row programs; K slots (WK) only for the rows OUTSIDE the GEMM band; NPR = row stride of the set-point arrays
+  int y_lo, y_hi;        // rows [y_lo, y_hi) take their linear term from the GEMM result Y (the band of dense rows)
   const T* vals;         // [n_inst][coef_stride]
   const T* Y;            // [P][NR] GEMM result K'.X
   const T* X;            // [P][NR] stage vector the derivative is evaluated at
@@ -56,13 +57,18 @@ __global__ void __launch_bounds__(32 * UPD_TG) stage_update_kernel(const UpdArgs
   const T* X = a.X + p0 * NR;
   const T* Pa = a.Pa + p0 * NPR;
   const T* Pb = a.Pb ? a.Pb + p0 * NPR : nullptr;
-  T y[U];
+  T y[U], q[U], sv[U];
   int inst[U];
+  // every HBM operand of the row is requested up front (Y, Q, S of U trajectories: 3 U independent loads in flight per
+  // thread) -- the kernel is bandwidth-bound and the row programs below only gather from the L1/L2-resident stage vector
 #pragma unroll
   for (int b = 0; b < U; ++b) {
     const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;      // clamp: lanes past the batch recompute the last one
     inst[b] = (int)((a.p_base + p) / a.E);
-    y[b] = a.Y[(p0 + b) * NR + r];                                      // arrays are padded to a multiple of U rows
+    const long long o = (p0 + b) * NR + r;                               // arrays are padded to a multiple of U rows
+    y[b] = (r >= a.y_lo && r < a.y_hi) ? a.Y[o] : T(0);
+    q[b] = a.Q[o];
+    sv[b] = a.stage >= 2 ? a.S[o] : T(0);
   }
   auto P = [&](int b, int c) -> T {
     const T v = Pa[(long long)b * NPR + c];
@@ -70,6 +76,15 @@ __global__ void __launch_bounds__(32 * UPD_TG) stage_update_kernel(const UpdArgs
   };
   const size_t cs = (size_t)tb.coef_stride;
   const T* v0 = a.vals + r;
+  // sparse rows (x' = v, probes ...): their few linear terms as a row program, in CSR order like the reference
+  for (int j = 0; j < w.x; ++j) {
+    const int col = __ldg(tb.k_col + j * NR + r);
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      const T kv = __ldg(v0 + inst[b] * cs + (size_t)j * NR);
+      y[b] = fma(kv, X[(long long)b * NR + col], y[b]);
+    }
+  }
   size_t off = (size_t)tb.WK * NR;
   for (int j = 0; j < w.y; ++j) {
     const int2 ix = __ldg(tb.g_idx + j * NR + r);
@@ -109,12 +124,11 @@ __global__ void __launch_bounds__(32 * UPD_TG) stage_update_kernel(const UpdArgs
 #pragma unroll
   for (int b = 0; b < U; ++b) {
     const long long o = (p0 + b) * NR + r;
-    const T q = a.Q[o];
     T xn;
-    if (a.stage == 1) { a.S[o] = y[b]; xn = fma(a.h2, y[b], q); }
-    else if (a.stage == 2) { a.S[o] = fma(T(2), y[b], a.S[o]); xn = fma(a.h2, y[b], q); }
-    else if (a.stage == 3) { a.S[o] = fma(T(2), y[b], a.S[o]); xn = fma(a.h, y[b], q); }
-    else { xn = fma(a.h6, a.S[o] + y[b], q); a.Q[o] = xn; }
+    if (a.stage == 1) { a.S[o] = y[b]; xn = fma(a.h2, y[b], q[b]); }
+    else if (a.stage == 2) { a.S[o] = fma(T(2), y[b], sv[b]); xn = fma(a.h2, y[b], q[b]); }
+    else if (a.stage == 3) { a.S[o] = fma(T(2), y[b], sv[b]); xn = fma(a.h, y[b], q[b]); }
+    else { xn = fma(a.h6, sv[b] + y[b], q[b]); a.Q[o] = xn; }
     a.Xn[o] = xn;
     if constexpr (sizeof(T) == 4) {
       if (a.Xn_hi) {

@@ -17,14 +17,18 @@
 namespace pasif_tc {
 
 constexpr int TC_BM = 128;          // trajectories per tile (UMMA M)
-constexpr int TC_BN = 192;          // rows of K' per tile   (UMMA N)
 constexpr int TC_BK = 32;           // floats per k-block (128 bytes)
-constexpr int TC_STAGES = 2;
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB (one of hi / lo)
-constexpr int TC_B_BYTES = TC_BN * TC_BK * 4;          // 24 KB
-constexpr int TC_STAGE_BYTES = 2 * TC_A_BYTES + 2 * TC_B_BYTES;
-constexpr int TC_SMEM = TC_STAGES * TC_STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
-constexpr int TC_TMEM_COLS = 256;   // power of two >= TC_BN
+// BN = rows of K' per tile (UMMA N): 192 for a full operator (544 rows = 3 tiles), 128 when only a band of dense rows goes
+// through the GEMM (256 rows = 2 tiles, no padding work); the narrower tile leaves room for a third pipeline stage
+template <int BN>
+struct TcCfg {
+  static constexpr int STAGES = BN <= 128 ? 3 : 2;
+  static constexpr int B_BYTES = BN * TC_BK * 4;        // 24 KB / 16 KB
+  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
+  static constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;   // power of two >= BN
+};
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -69,12 +73,16 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 }
 
 // grid (m tiles, p tiles), 128 threads.  mapA*: X hi / lo [Ppad][K]; mapB*: Kd hi / lo [Mpad][K]; p_row0: first row of
-// this launch's part inside the X arrays; Y is already offset to the part.
+// this launch's part inside the X arrays; Y is already offset to the part.  Rows [m_base, M) of K' are computed
+// (m_base a multiple of 32: the band of dense rows; Y columns outside it are not touched).
+template <int TC_BN>
 __global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAh,
                                                                          const __grid_constant__ CUtensorMap mapAl,
                                                                          const __grid_constant__ CUtensorMap mapBh,
                                                                          const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y,
-                                                                         int M, int K, int ldy, int p_row0) {
+                                                                         int M, int K, int ldy, int p_row0, int m_base) {
+  constexpr int TC_STAGES = TcCfg<TC_BN>::STAGES, TC_B_BYTES = TcCfg<TC_BN>::B_BYTES, TC_STAGE_BYTES = TcCfg<TC_BN>::STAGE_BYTES,
+                TC_TMEM_COLS = TcCfg<TC_BN>::TMEM_COLS;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
@@ -82,7 +90,7 @@ __global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const _
   uint64_t* done = empty + TC_STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.x * TC_BN;
+  const int m0 = m_base + blockIdx.x * TC_BN;
   const int p0 = blockIdx.y * TC_BM;
   const int nkb = K / TC_BK;
 
