@@ -97,3 +97,60 @@ def test_membrane_through_lane_groups_matches_oracle(shape, prec):
     assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
     assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
     assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_full_size_chain_properties(prec):
+    """BASELINE config 4 at its full component size (256-DOF chain, 514 states, 518 adjoint states) through size-independent
+    properties: duplicated excitations give bit-identical rows, the split and the tile kernels agree, the excitation-summed
+    gradient equals the sum of the rows, and a second call reproduces the first bit for bit."""
+    s = wl.chain_system(256)
+    exc = wl.random_sine_excitations(256, 240, 16000, seed=11)
+    case = dict(systems=[s], jacobians=[wl.chain_jacobian(s, 4)], excitations=np.concatenate([exc, exc]), sample_rate=16000,
+                numsteps=0, interp=None, traj_save_steps=None)
+    a = run_case(capi.engine_class(prec), case)
+    p = a["_p"]
+    assert p._query("lane_classes") >= 2 and p._query("lane_G") == (64 if prec == "f64" else 32)
+    n, na, E = 514, 518, 512
+    amp, grad = a["amplitudes"].reshape(E, n), a["gradient"].reshape(E, na)
+    assert np.array_equal(amp[:256], amp[256:]) and np.array_equal(grad[:256], grad[256:])
+    assert np.array_equal(a["amplitudes"], a["amplitudes_2nd"])
+    assert np.array_equal(np.asarray(p.getGradient()), a["gradient"])
+    assert np.all(np.isfinite(amp)) and np.all(np.isfinite(grad)) and np.max(np.abs(grad)) > 0
+    red = np.asarray(p._getGradientReduced(0))
+    assert rel_err(red, grad.sum(axis=0)) < (1e-12 if prec == "f64" else 2e-5)
+    t = run_case(capi.engine_class(prec), case, options={"lanes": "off"})
+    assert t["_p"]._query("lane_classes") == 0
+    assert close(a["amplitudes"], t["amplitudes"], n, prec, TOL_FWD)
+    assert close(a["gradient"], t["gradient"], na, prec, TOL_ADJ)
+
+
+def test_gradient_through_lane_groups_matches_finite_differences():
+    """exact (clean) schedule: d p1(T) / d Lambda_k from the adjoint sweep of a 60-DOF chain against a central finite
+    difference of the forward probe -- the gradient the adjoint builder promises (pasif_b200/adjoint.py).  The adjoint ODE is
+    integrated with the reference's scheme (forward state averaged at the half stages), which is not the algebraic
+    transpose of the forward RK4 map: agreement is to discretisation error (4e-5 with the C oracle), not round-off."""
+    s = wl.chain_system(60)
+    exc = wl.random_sine_excitations(3, 400, 16000, seed=13)
+    base = dict(excitations=exc, sample_rate=16000, numsteps=0, interp=None, traj_save_steps=None)
+    a = run_case(capi.engine_class("f64", "clean"), dict(base, systems=[s], jacobians=[wl.chain_jacobian(s, 2)]))
+    assert a["_p"]._query("lane_classes") >= 2
+    n = s["n"]
+    g = a["gradient"].reshape(3, n + 2)[:, n:]                    # two parameters: Lambda'_0, Lambda'_1 (pre-scaled)
+    M = np.asarray(s["M"], dtype=np.float64)
+    lidx = np.asarray(s["Lambda"][2]).reshape(-1, 4)
+    for k in range(2):
+        out_row = int(lidx[k, 0])
+        vals = []
+        for sign in (+1, -1):
+            s2 = dict(s)
+            lv = list(s["Lambda"][1])
+            # pre-scaled coefficient Lambda' = -Lambda / M[out]: a step d in Lambda' is a step -d * M[out] in Lambda
+            lam_p = -lv[k] / M[out_row]
+            h = 1e-4 * abs(lam_p)
+            lv[k] = -(lam_p + sign * h) * M[out_row]
+            s2["Lambda"] = (s["Lambda"][0], lv, s["Lambda"][2])
+            f = run_case(capi.engine_class("f64"), dict(base, systems=[s2], jacobians=None), want_grad=False)
+            vals.append(f["amplitudes"].reshape(3, n)[:, n - 1])   # p1(T)
+        fd = (vals[0] - vals[1]) / (2 * h)
+        assert np.max(np.abs(fd - g[:, k])) < 1e-3 * max(np.max(np.abs(fd)), 1e-30), (k, fd, g[:, k])
