@@ -50,6 +50,12 @@ WORKLOADS = {
                 name="C4 dense: 256-DOF system with dense shared K, B (514 states) x 16384 excitations x 128 RK4 steps, forward + adjoint"),
 }
 
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the hot kernels, from one `ncu --set full` capture of the same
+# command at the workload's full size (profiles/r01_ncu_c3_full_config_kernels.csv: chunk of 317 steps x 262144 trajectories;
+# algorithmic bytes of that launch: 317 x 262144 x 4 needed variables x 4 B = 1.330e9)
+NCU_TRAFFIC = {("c3", "f32", "reference"): {"gfwd": 1.270203e9 + 0.008973e9, "bwd": 1.346701e9 + 0.013820e9,
+                                            "source": "profiles/r01_ncu_c3_full_config_kernels.csv"}}
+
 # algorithmic flops per trajectory-step of the 8-state system / 12-state Jacobian:
 #   D = 2 nnzK + 3 nnzG + 4 nnzL + 5 nnzP + 2 nnzF ; forward step 4 D + 13 N ; adjoint step 4 D_adj + 13 N_adj + 2 N
 F_FWD, F_BWD = 240.0, 380.0
@@ -493,6 +499,11 @@ def main():
                 "ms_per_step": e2e_t / a.steps * 1e3, "parts": e2e_parts},
         "gpu_launches": launches, "clocks": clocks, "wall_s_grad_steps": wall_grad,
     }
+    tr = NCU_TRAFFIC.get((a.workload, w["dtype"], a.compat))
+    if tr and not (a.systems or a.length or a.excitations) and not large:
+        line["roofline"]["traffic"] = tr[dom]
+        line["roofline"]["traffic_source"] = tr["source"] + " (ncu --set full, same command; bytes per launch of the dominant kernel)"
+        line["roofline"]["algorithmic_bytes_per_launch"] = pairs * c * N_NEEDED * sz
     if lane:
         line["config"]["lane_split"] = {k: p._query("lane_" + k) for k in ("G", "R", "RA", "nv", "nc_fwd", "nc_adj", "halo_fwd", "halo_adj", "halo_p", "efficiency")}
         line["config"]["path"] = "lane-block register kernels (lane_split.hpp): G threads per trajectory, state in registers, halo exchange per stage"
