@@ -266,6 +266,12 @@ def main():
     if a.impl == "reference":
         return run_reference_arm(a, w)
 
+    # stdout carries exactly ONE line (the JSON): anything a library prints there while the run is set up (NCCL's version
+    # banner under NCCL_DEBUG=VERSION, for one) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
     import torch
     from pasif_b200 import capi, frontend, workloads as wl
     rank = int(os.environ.get("RANK", "0"))
@@ -520,7 +526,8 @@ def main():
         v, fv, sample, _ = cpu_baseline_sample(w, threads)
         line["cpu_baseline"] = {"value": v, "unit": "gradient evals/s", "cores": threads, "kind": "port", "sample": sample,
                                 "forward_system_steps_per_s": fv}
-    print(json.dumps(line))
+    sys.stdout.flush()
+    os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if dist is not None:
         dist.destroy_process_group()
 
