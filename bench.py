@@ -247,6 +247,7 @@ def main():
                     help="adjoint schedule: the reference's literal one (default, parity with its outputs) or the exact "
                          "discrete adjoint, whose chunk trajectories are kept from the forward sweep as far as HBM allows")
     ap.add_argument("--tail-budget-gb", default="auto", help="clean schedule: device memory for kept chunk trajectories")
+    ap.add_argument("--option", action="append", default=[], help="engine option key=value (debug), repeatable")
     ap.add_argument("--stage-parts", default="", help="dense-operator path: number of batch parts on their own streams (debug)")
     ap.add_argument("--lane-regs", default="", help="register estimate up to which a lane pattern is accepted (debug)")
     ap.add_argument("--lanes", default="on", help="lane-block split of large components: on | off | widest group (8..128)")
@@ -313,6 +314,9 @@ def main():
         p._setOption("lane_regs", a.lane_regs)
     if a.stage_parts:
         p._setOption("stage_parts", a.stage_parts)
+    for kv in a.option:
+        k, v = kv.split("=", 1)
+        p._setOption(k, v)
     t_setup = time.time()
     p.setSystems(*wl.to_frontend_args(systems, mod))
     p.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
@@ -448,8 +452,8 @@ def main():
         mult = 3 if w["dtype"] == "f32" else 1
         ppad = pad(pairs, 128)
         # the GEMM covers the band of dense rows of K' (x' = v rows and probes stay row programs): rows x padded columns
-        gemm_flops = {"gfwd": 2.0 * p._query("stage_band_rows_fwd") * pad(N_FWD, 32) * ppad * mult,
-                      "bwd": 2.0 * p._query("stage_band_rows_adj") * pad(N_ADJ, 32) * ppad * mult}
+        gemm_flops = {"gfwd": 2.0 * p._query("stage_band_rows_fwd") * p._query("stage_band_cols_fwd") * ppad * mult,
+                      "bwd": 2.0 * p._query("stage_band_rows_adj") * p._query("stage_band_cols_adj") * ppad * mult}
         if w["dtype"] == "f32":
             tpeak = peaks.get("bf16_tflops", 1590.0) / 2.0
             tsrc = "tf32 dense = half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2" if peaks else "fallback 1590 / 2"
@@ -463,6 +467,7 @@ def main():
                   "traffic": None, "peak_source": tsrc, "tensor_products_per_useful_product": mult,
                   "useful_tflops": ach / mult, "gemm_us_per_launch": per_kernel[dom]["avg_launch_ms"] * 1e3,
                   "gemm_rows": {"fwd": p._query("stage_band_rows_fwd"), "adj": p._query("stage_band_rows_adj")},
+                  "gemm_cols": {"fwd": p._query("stage_band_cols_fwd"), "adj": p._query("stage_band_cols_adj")},
                   "gemm_share_of_step": (k_ms["gfwd"] + k_ms["bwd"]) / max(serial_ms, 1e-9),
                   "whole_step": {"achieved": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12,
                                  "frac": (flops_gfwd + flops_bwd) / (dev_ms / a.steps * 1e-3) / 1e12 / (tpeak / mult)},

@@ -396,6 +396,7 @@ struct pasif_engine {
   // dense-operator path: the batch is cut into `stage_nparts` parts, each with its own stream, so that the tensor-bound
   // GEMM of one part overlaps the HBM-bound update of another (part 0 runs on `stream`)
   int stage_nparts = 4;
+  int update_u = 4;                              // trajectories per thread of the dense-operator path's update kernel
   std::vector<cudaStream_t> part_streams;
   std::vector<cudaEvent_t> part_events;
   bool overlap = true;
@@ -1207,6 +1208,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     const int n = std::atoi(v.c_str());
     if (n < 1 || n > 16) throw std::runtime_error("stage_parts must be in [1, 16]");
     e->stage_nparts = n;
+  } else if (k == "update_u") {
+    e->update_u = std::atoi(v.c_str());
   } else if (k == "gemm_band") {
     e->gemm_band = (v == "on" || v == "1");
   } else if (k == "tcgen05") {
@@ -1309,14 +1312,17 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
-  else if (k == "stage_band_rows_fwd" || k == "stage_band_rows_adj") {
-    // rows of K' that go through the per-stage GEMM of the (first) dense-operator class
+  else if (k.rfind("stage_band_", 0) == 0) {
+    // rows / columns of K' that go through the per-stage GEMM of the (first) dense-operator class:
+    // stage_band_rows_fwd | stage_band_rows_adj | stage_band_cols_fwd | stage_band_cols_adj
     *value = 0;
+    const bool fwd = k.size() > 4 && k.compare(k.size() - 4, 4, "_fwd") == 0;
+    const bool rows = k.find("_rows_") != std::string::npos;
     for (auto* v : {&e->joint_classes, &e->fwd_classes})
       for (auto& c : *v)
         if (*value == 0 && c.large && c.large->stage) {
-          const LargeSide& sd = k == "stage_band_rows_fwd" ? c.large->fwd : c.large->adj;
-          *value = (double)(sd.band_hi - sd.band_lo);
+          const LargeSide& sd = fwd ? c.large->fwd : c.large->adj;
+          *value = rows ? (double)(sd.band_hi - sd.band_lo) : (double)(sd.kband_hi - sd.kband_lo);
         }
   }
   else if (k == "aot_table_size") *value = (double)aot_table().size();

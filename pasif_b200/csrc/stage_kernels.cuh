@@ -206,8 +206,9 @@ __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commi
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
+// lda / ldb: row strides of A / B (both pointers already offset to the first column of the K band)
 __global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B,
-                                                            double* __restrict__ Y, int M, int K, int ldy) {
+                                                            double* __restrict__ Y, int M, int K, int ldy, int lda, int ldb) {
   extern __shared__ __align__(16) unsigned char dg_smem[];
   double* sA = reinterpret_cast<double*>(dg_smem);                    // [STAGES][BM][LD]
   double* sB = sA + DG_STAGES * DG_BM * DG_LD;                        // [STAGES][BN][LD]
@@ -216,8 +217,8 @@ __global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __rest
   const int wm = warp >> 2, wn = warp & 3;
   const int m0 = blockIdx.x * DG_BM;
   const long long p0 = (long long)blockIdx.y * DG_BN;
-  const double* Ag = A + (size_t)m0 * K;
-  const double* Bg = B + (size_t)p0 * K;
+  const double* Ag = A + (size_t)m0 * lda;
+  const double* Bg = B + (size_t)p0 * ldb;
   const int nkb = K / DG_BK;
 
   auto issue = [&](int kb, int st) {
@@ -227,12 +228,12 @@ __global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __rest
 #pragma unroll
     for (int c = tid; c < DG_BM * 8; c += 256) {
       const int row = c >> 3, ch = c & 7;
-      cp_async16(a + row * DG_LD + ch * 2, Ag + (size_t)row * K + kb * DG_BK + ch * 2);
+      cp_async16(a + row * DG_LD + ch * 2, Ag + (size_t)row * lda + kb * DG_BK + ch * 2);
     }
 #pragma unroll
     for (int c = tid; c < DG_BN * 8; c += 256) {
       const int row = c >> 3, ch = c & 7;
-      cp_async16(b + row * DG_LD + ch * 2, Bg + (size_t)row * K + kb * DG_BK + ch * 2);
+      cp_async16(b + row * DG_LD + ch * 2, Bg + (size_t)row * ldb + kb * DG_BK + ch * 2);
     }
   };
 
@@ -292,7 +293,7 @@ constexpr int SG_SMEM = SG_STAGES * 2 * (SG_BM + SG_BN) * SG_LD * 4;
 
 __global__ void __launch_bounds__(256) sgemm_tn_3xtf32_kernel(const float* __restrict__ Ahi, const float* __restrict__ Alo,
                                                               const float* __restrict__ Bhi, const float* __restrict__ Blo,
-                                                              float* __restrict__ Y, int M, int K, int ldy) {
+                                                              float* __restrict__ Y, int M, int K, int ldy, int lda, int ldb) {
   extern __shared__ __align__(16) unsigned char dg_smem[];
   float* sAh = reinterpret_cast<float*>(dg_smem);                     // [STAGES][BM][LD]
   float* sAl = sAh + SG_STAGES * SG_BM * SG_LD;
@@ -309,13 +310,13 @@ __global__ void __launch_bounds__(256) sgemm_tn_3xtf32_kernel(const float* __res
     // rows of 16 floats = 4 chunks of 16 bytes
     for (int c = tid; c < SG_BM * 4; c += 256) {
       const int row = c >> 2, ch = c & 3;
-      const size_t go = (size_t)(m0 + row) * K + kb * SG_BK + ch * 4;
+      const size_t go = (size_t)(m0 + row) * lda + kb * SG_BK + ch * 4;
       cp_async16(sAh + (st * SG_BM + row) * SG_LD + ch * 4, Ahi + go);
       cp_async16(sAl + (st * SG_BM + row) * SG_LD + ch * 4, Alo + go);
     }
     for (int c = tid; c < SG_BN * 4; c += 256) {
       const int row = c >> 2, ch = c & 3;
-      const size_t go = (size_t)(p0 + row) * K + kb * SG_BK + ch * 4;
+      const size_t go = (size_t)(p0 + row) * ldb + kb * SG_BK + ch * 4;
       cp_async16(sBh + (st * SG_BN + row) * SG_LD + ch * 4, Bhi + go);
       cp_async16(sBl + (st * SG_BN + row) * SG_LD + ch * 4, Blo + go);
     }

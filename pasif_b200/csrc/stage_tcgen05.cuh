@@ -74,13 +74,14 @@ __device__ __forceinline__ void umma_commit(uint64_t* bar) {
 
 // grid (m tiles, p tiles), 128 threads.  mapA*: X hi / lo [Ppad][K]; mapB*: Kd hi / lo [Mpad][K]; p_row0: first row of
 // this launch's part inside the X arrays; Y is already offset to the part.  Rows [m_base, M) of K' are computed
-// (m_base a multiple of 32: the band of dense rows; Y columns outside it are not touched).
+// (m_base a multiple of 32: the band of dense rows; Y columns outside it are not touched) over the K columns
+// [k_base, k_base + K) (multiples of 32: the band of columns those rows use).
 template <int TC_BN>
 __global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const __grid_constant__ CUtensorMap mapAh,
                                                                          const __grid_constant__ CUtensorMap mapAl,
                                                                          const __grid_constant__ CUtensorMap mapBh,
                                                                          const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y,
-                                                                         int M, int K, int ldy, int p_row0, int m_base) {
+                                                                         int M, int K, int ldy, int p_row0, int m_base, int k_base) {
   constexpr int TC_STAGES = TcCfg<TC_BN>::STAGES, TC_B_BYTES = TcCfg<TC_BN>::B_BYTES, TC_STAGE_BYTES = TcCfg<TC_BN>::STAGE_BYTES,
                 TC_TMEM_COLS = TcCfg<TC_BN>::TMEM_COLS;
   extern __shared__ unsigned char tc_smem_raw[];
@@ -120,10 +121,10 @@ __global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const _
       mbar_wait(&empty[s], ph ^ 1);                       // first pass: succeeds immediately (preceding phase)
       unsigned char* st = base + s * TC_STAGE_BYTES;
       mbar_expect_tx(&full[s], TC_STAGE_BYTES);
-      tma_load_2d(st, &mapAh, &full[s], kb * TC_BK, p_row0 + p0);
-      tma_load_2d(st + TC_A_BYTES, &mapAl, &full[s], kb * TC_BK, p_row0 + p0);
-      tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], kb * TC_BK, m0);
-      tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], kb * TC_BK, m0);
+      tma_load_2d(st, &mapAh, &full[s], k_base + kb * TC_BK, p_row0 + p0);
+      tma_load_2d(st + TC_A_BYTES, &mapAl, &full[s], k_base + kb * TC_BK, p_row0 + p0);
+      tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], k_base + kb * TC_BK, m0);
+      tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], k_base + kb * TC_BK, m0);
     }
   } else if (warp == 1 && lane == 0) {
     // ---- MMA issuer
