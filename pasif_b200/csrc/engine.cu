@@ -404,6 +404,7 @@ struct pasif_engine {
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
   int lanes_max = 128;                           // widest thread group of the lane-block split (0: off)
+  int one_thread_regs = 330;                     // register estimate above which a component is offered to the lane-block split
   int lane_regs = 240;                           // register estimate a lane pattern may reach before a wider group is tried
   long long lane_classes = 0;
   LaneSplitReport lane_report;                   // of the last class that was split
@@ -605,7 +606,11 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
   for (size_t i = 0; i < cds.size(); ++i) {
     DevClass& dc = out[i];
     dc.h = std::move(cds[i]);
-    if (is_large(E, dc.h) && E.lanes_max >= 8) {
+    // offered to every component that is too large for one thread -- by its size (large_threshold) or because state +
+    // coefficients of the one-thread kernel would not fit the register file (it would spill every step)
+    const bool spills = std::max((long long)dc.h.fwd.nc() + 4ll * dc.h.fwd.N, dc.h.joint ? (long long)dc.h.adj.nc() + 4ll * dc.h.adj.N : 0ll) *
+                                (long long)(sizeof(T) / 4) + 24 > E.one_thread_regs;
+    if ((is_large(E, dc.h) || spills) && E.lanes_max >= 8) {
       // lane-block split (lane_split.hpp): the component becomes n_inst * G virtual instances of one lane-local pattern
       // that the register-resident kernels integrate with G threads per trajectory; components it does not suit
       // (dense operators, irregular coupling) stay with the tile kernels / the dense-operator path below
@@ -1216,6 +1221,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
     e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 128 : std::atoi(v.c_str()));
+  } else if (k == "one_thread_regs") {
+    e->one_thread_regs = std::atoi(v.c_str());
   } else if (k == "lane_regs") {
     e->lane_regs = std::atoi(v.c_str());
   } else if (k == "large_threshold") {

@@ -154,3 +154,19 @@ def test_gradient_through_lane_groups_matches_finite_differences():
             vals.append(f["amplitudes"].reshape(3, n)[:, n - 1])   # p1(T)
         fd = (vals[0] - vals[1]) / (2 * h)
         assert np.max(np.abs(fd - g[:, k])) < 1e-3 * max(np.max(np.abs(fd)), 1e-30), (k, fd, g[:, k])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_mid_size_component_is_split_when_one_thread_would_spill(prec):
+    """16-DOF chain (34 states, below large_threshold): in fp64 state + coefficients of the one-thread kernel need ~560
+    registers, so the component is offered to the lane-block split (measured 16x on the gradient); in fp32 it still fits one
+    thread.  Both must reproduce the oracle."""
+    case = chain_case(16, False, E=9, L=500)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("lane_classes") == (2 if prec == "f64" else 0)
+    assert a["_p"]._query("large_classes") == 0
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)

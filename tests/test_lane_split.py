@@ -50,6 +50,9 @@ def test_dense_operator_and_small_systems_are_not_split():
     assert p._query("lane_classes") == 0                           # left to the dense-operator (tensor-core) path
     p = _host("f64", [wl.fit8_system()], [wl.fit8_jacobian()])
     assert p._query("lane_classes") == 0                           # register-resident: one thread per trajectory
+    s = wl.chain_system(16)                                        # 34 states: fits one thread in fp32, would spill in fp64
+    assert _host("f32", [s], [wl.chain_jacobian(s, 3)])._query("lane_classes") == 0
+    assert _host("f64", [s], [wl.chain_jacobian(s, 3)])._query("lane_classes") == 2
     s = wl.chain_system(40)
     p = _host("f32", [s], None, {"lanes": "off"})
     assert p._query("lane_classes") == 0
