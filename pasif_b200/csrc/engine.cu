@@ -370,8 +370,13 @@ struct DevClass {
 
 }  // namespace
 
+namespace {
+struct StageBufs;   // work arrays of the dense-operator path (stage_host.inc)
+}
+
 struct pasif_engine {
   int dtype = PASIF_F64, device = 0;
+  StageBufs* stage_bufs[2] = {nullptr, nullptr};
   bool host_only = false;
   uint32_t E = 0, L = 0, sample_rate = 1, numsteps = 0;
   bool have_exc = false;
@@ -1105,6 +1110,8 @@ void pasif_destroy(pasif_engine* e) {
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
     }
     if (e->stream2) cudaStreamDestroy(e->stream2);
+    for (StageBufs*& sb : e->stage_bufs)
+      if (sb) { sb->release(); delete sb; sb = nullptr; }
     for (cudaStream_t st : e->part_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : e->part_events) cudaEventDestroy(ev);
     if (e->stream) cudaStreamSynchronize(e->stream);

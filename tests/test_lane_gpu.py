@@ -170,3 +170,38 @@ def test_mid_size_component_is_split_when_one_thread_would_spill(prec):
     assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
     assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
     assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lane_groups_with_interpolated_excitations(prec):
+    """interpolation table (two force sub-samples per RK4 step, preprocessed half-step stream) through the lane groups"""
+    case = chain_case(40, False, E=5, L=260)
+    case["interp"] = (wl.linear_interpolation_table(8), 8)
+    case["sample_rate"] = 4 * 16000
+    case["numsteps"] = 4 * 250
+    case["traj_save_steps"] = 100
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("lane_classes") >= 2
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_lane_groups_hbm_sized_schedule_is_bit_identical(prec):
+    """exact schedule: chunk trajectories of the lane classes kept from the forward sweep (tail_budget_gb) leave every bit
+    of the gradient unchanged and save recompute launches; `save` stops the literal schedule after a chunk"""
+    case = chain_case(40, False, E=6, L=900)
+    ref = run_case(capi.engine_class(prec, "clean"), case, want_traj=False, options={"tail_budget_gb": "0"})
+    assert ref["_p"]._query("lane_classes") >= 2 and ref["_p"]._query("stored_chunks") == 0
+    out = run_case(capi.engine_class(prec, "clean"), case, want_traj=False, options={"tail_budget_gb": "1.0"})
+    assert out["_p"]._query("stored_chunks") == out["_p"]._query("chunks") > 0
+    assert np.array_equal(out["gradient"], ref["gradient"])
+    assert out["_p"]._query("last_launches") < ref["_p"]._query("last_launches")
+    lit = run_case(capi.engine_class(prec, "reference"), case, want_traj=False)
+    part = np.asarray(lit["_p"].getGradient(20))                  # stop after chunk 20 of 30: a different, finite state
+    assert part.shape == lit["gradient"].shape and np.all(np.isfinite(part)) and not np.array_equal(part, lit["gradient"])
+    o = run_case(_oracle(prec, "reference"), case, want_traj=False)
+    assert close(part, np.asarray(o["_p"].getGradient(20)), case["jacobians"][0]["n"], prec, TOL_ADJ)
