@@ -40,7 +40,7 @@ def build_library(force=False, verbose=False):
            [os.path.join(os.path.dirname(HERE), "include", "pasif_b200.h")]
     if not force and _newer(LIB, srcs):
         return LIB
-    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu"), "-ldl"]
+    cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "engine.cu"), "-ldl", "-lpthread"]
     out = _run(cmd)
     if verbose:
         print(out)

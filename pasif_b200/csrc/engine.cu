@@ -22,6 +22,7 @@
 #include <fstream>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/pasif_b200.h"
@@ -731,6 +732,20 @@ void end_timing(pasif_engine& E) {
 
 constexpr size_t kStageSlot = 8u << 20;
 
+// host-side copy / widening split over a few threads: one core moves ~10 GB/s between pageable and pinned memory, which
+// would make the staging copy -- not the DMA -- the bottleneck of a large hand-off (C4: 262 MB of excitations per call)
+template <typename F>
+void host_parallel(size_t n, size_t grain, F&& fn) {          // fn(begin, end) over [0, n)
+  unsigned nt = std::min<unsigned>(4, std::max(1u, std::thread::hardware_concurrency() / 2));
+  if (n < 2 * grain || nt < 2) { fn((size_t)0, n); return; }
+  nt = (unsigned)std::min<size_t>(nt, n / grain);
+  const size_t per = (n + nt - 1) / nt;
+  std::vector<std::thread> th;
+  for (unsigned i = 1; i < nt; ++i) th.emplace_back([&, i] { fn(std::min(n, i * per), std::min(n, (i + 1) * per)); });
+  fn((size_t)0, std::min(n, per));
+  for (auto& t : th) t.join();
+}
+
 double wall_ms() {
   timespec ts;
   clock_gettime(CLOCK_MONOTONIC, &ts);
@@ -748,7 +763,8 @@ void h2d_staged(pasif_engine& E, void* dst, const void* src, size_t bytes) {
     const int slot = (int)(i & 1);
     char* h = (char*)E.h_stage.p + slot * kStageSlot;
     CUDA_CHECK(cudaEventSynchronize(E.ev_stage[slot]));          // the DMA that last read this slot has finished
-    std::memcpy(h, (const char*)src + off, len);
+    const char* sp = (const char*)src + off;
+    host_parallel(len, (size_t)1 << 20, [&](size_t b, size_t e) { std::memcpy(h + b, sp + b, e - b); });
     CUDA_CHECK(cudaMemcpyAsync((char*)dst + off, h, len, cudaMemcpyHostToDevice, E.stream));
     CUDA_CHECK(cudaEventRecord(E.ev_stage[slot], E.stream));
   }
@@ -780,8 +796,10 @@ void download(pasif_engine& E, const void* dev, double* out, uint64_t n) {
     const T* h = (const T*)((const char*)E.h_stage.p + slot * kStageSlot);
     const uint64_t len = std::min(per, n - c * per);
     double* o = out + c * per;
-    if (sizeof(T) == sizeof(double)) std::memcpy(o, h, len * sizeof(double));
-    else for (uint64_t i = 0; i < len; ++i) o[i] = (double)h[i];
+    host_parallel((size_t)len, (size_t)1 << 18, [&](size_t b, size_t e) {
+      if (sizeof(T) == sizeof(double)) std::memcpy(o + b, h + b, (e - b) * sizeof(double));
+      else for (size_t i = b; i < e; ++i) o[i] = (double)h[i];
+    });
   }
   E.last_d2h_ms = wall_ms() - t0;
 }
