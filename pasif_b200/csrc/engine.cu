@@ -409,7 +409,8 @@ struct pasif_engine {
   std::string err;
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
-  int lanes_max = 128;                           // widest thread group of the lane-block split (0: off)
+  int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
+  int lane_minb_fwd = 0, lane_minb_bwd = 0;      // lane-block kernels: minimum CTAs per SM handed to __launch_bounds__ (0: none)
   int one_thread_regs = 330;                     // register estimate above which a component is offered to the lane-block split
   int lane_regs = 240;                           // register estimate a lane pattern may reach before a wider group is tried
   long long lane_classes = 0;
@@ -453,18 +454,22 @@ void upload_int(DevBuf& b, const std::vector<int>& v) {
 }
 
 // ---- kernel lookup: prebuilt table first, NVRTC otherwise
-std::string jit_source(const ClassData& c, int dtype) {
-  std::string s = kernel_header_text();
+std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb_bwd = 0) {
+  // lane groups wider than the default CTA are compiled for a CTA of their own width
+  std::string s = c.lanes > PASIF_BLOCK ? "#define PASIF_BLOCK " + std::to_string(c.lanes) + "\n" : std::string();
+  s += kernel_header_text();
   s += "\n";
   s += emit_class_traits(c);
   const char* T = dtype == PASIF_F32 ? "float" : "double";
+  // minb > 0: __launch_bounds__(PASIF_BLOCK, minb) -- caps the registers so that `minb` CTAs fit an SM (lane-block classes)
+  auto lb = [](int minb) { return minb > 0 ? "__launch_bounds__(PASIF_BLOCK, " + std::to_string(minb) + ")" : std::string("__launch_bounds__(PASIF_BLOCK)"); };
   if (!c.joint) {
-    s += std::string("extern \"C\" __global__ void __launch_bounds__(PASIF_BLOCK) pasif_k_fwd(const pasif::FwdArgs<") + T +
+    s += std::string("extern \"C\" __global__ void ") + lb(minb_fwd) + " pasif_k_fwd(const pasif::FwdArgs<" + T +
          "> a) { pasif::forward_body<" + T + ", " + c.name + ", pasif::NoDense>(a); }\n";
   } else {
-    s += std::string("extern \"C\" __global__ void __launch_bounds__(PASIF_BLOCK) pasif_k_gfwd(const pasif::FwdArgs<") + T +
+    s += std::string("extern \"C\" __global__ void ") + lb(minb_fwd) + " pasif_k_gfwd(const pasif::FwdArgs<" + T +
          "> a) { pasif::forward_body<" + T + ", " + c.name + "::Fwd, " + c.name + "::Adj>(a); }\n";
-    s += std::string("extern \"C\" __global__ void __launch_bounds__(PASIF_BLOCK) pasif_k_bwd(const pasif::BwdArgs<") + T +
+    s += std::string("extern \"C\" __global__ void ") + lb(minb_bwd) + " pasif_k_bwd(const pasif::BwdArgs<" + T +
          "> a) { pasif::backward_body<" + T + ", " + c.name + "::Adj>(a); }\n";
   }
   return s;
@@ -538,7 +543,7 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
                              std::to_string(c.fwd.nc() + c.adj.nc()) + " coefficients: beyond the register-resident "
                              "kernel's range (<= 48 variables); the shared-memory large-system path is not built yet");
   g_drv.load();
-  std::vector<char> cubin = jit_compile(E, jit_source(c, E.dtype));
+  std::vector<char> cubin = jit_compile(E, jit_source(c, E.dtype, c.lanes > 1 ? E.lane_minb_fwd : 0, c.lanes > 1 ? E.lane_minb_bwd : 0));
   if (g_drv.ModuleLoadData(&dc.module, cubin.data()) != CUDA_SUCCESS)
     throw std::runtime_error("cuModuleLoadData failed for the specialised kernel of " + c.name);
   auto getf = [&](const char* n, CUfunction* f) {
@@ -573,7 +578,7 @@ void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& a
   if (!k.valid()) throw std::runtime_error("internal: kernel handle not resolved");
   if (!st) st = E.stream;
   // lane-block classes: a group of `lanes` threads must sit in one CTA; they are compiled for the full block
-  const unsigned block = lanes > 1 ? (unsigned)PASIF_BLOCK : pick_block(E, n_threads);
+  const unsigned block = lanes > 1 ? (unsigned)std::max(PASIF_BLOCK, lanes) : pick_block(E, n_threads);
   const unsigned grid = (unsigned)((n_threads + block - 1) / block);
   void* params[] = {(void*)&args};
   if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), st));
@@ -1245,7 +1250,11 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
   } else if (k == "tcgen05") {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
-    e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 128 : std::atoi(v.c_str()));
+    e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 1024 : std::atoi(v.c_str()));
+  } else if (k == "lane_minb_fwd") {
+    e->lane_minb_fwd = std::atoi(v.c_str());
+  } else if (k == "lane_minb_bwd") {
+    e->lane_minb_bwd = std::atoi(v.c_str());
   } else if (k == "one_thread_regs") {
     e->one_thread_regs = std::atoi(v.c_str());
   } else if (k == "lane_regs") {
@@ -1394,7 +1403,7 @@ int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t c
   const std::string a = std::string("--gpu-architecture=") + (arch ? arch : "sm_100a");
   for (auto* v : {&e->fwd_classes, &e->joint_classes})
     for (auto& c : *v) {
-      if (c.large) continue;
+      if (c.large || (c.h.lanes == 1 && is_large(*e, c.h))) continue;   // tile / dense-operator classes are prebuilt kernels
       const std::string src = jit_source(c.h, e->dtype);
       nvrtcProgram prog = nullptr;
       if (g_nvrtc.CreateProgram(&prog, src.c_str(), "pasif_jit.cu", 0, nullptr, nullptr) != 0) throw std::runtime_error("nvrtcCreateProgram failed");

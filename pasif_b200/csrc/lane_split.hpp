@@ -1,7 +1,7 @@
 // lane_split.hpp -- host-side partitioner of the LANE-BLOCK path (no CUDA in this file).
 //
 // A component with more coupled state variables than one thread can keep in registers (BASELINE config 4: a 256-DOF
-// chain, 514 states) is integrated by a GROUP of G threads (G = 8 .. 128 lanes): every lane owns R = ceil(N / G)-ish
+// chain, 514 states) is integrated by a GROUP of G threads (G = 8 .. 1024 lanes; above 128 the group is a whole CTA): every lane owns R = ceil(N / G)-ish
 // state variables in registers and evaluates their rows of the derivative; the few operands owned by other lanes
 // ("halo") are exchanged once per RK4 stage.  For the kernels this is just another pattern class: the big component of
 // n_inst instances becomes n_inst * G VIRTUAL instances (virtual instance = instance * G + lane) of ONE lane-local
@@ -487,9 +487,19 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   rep.regs_est = std::max(regs_f, regs_a);
   const double real = (double)F.nc() + (c.joint ? (double)c.adj.nc() : 0.0);
   rep.efficiency = real / ((double)G * (double)(rep.nc_fwd + rep.nc_adj));
+  // groups wider than the default CTA (128 threads) get a CTA of their own width: the register file then caps a thread at
+  // 65536 / G registers
+  if (G > 128) reg_budget = std::min(reg_budget, 65536 / G - 8);
   if (rep.regs_est > reg_budget) { rep.why = "register estimate " + std::to_string(rep.regs_est) + " > " + std::to_string(reg_budget); return false; }
   if (rep.efficiency < min_eff) { rep.why = "only " + std::to_string((int)(rep.efficiency * 100)) + " % of the common pattern's terms are real"; return false; }
   if (fa.R > 48 || (c.joint && aa.R > 48)) { rep.why = "more than 48 slots per lane"; return false; }
+  {
+    // static shared memory of the halo exchange: 2 buffers x published slots x CTA width, per exchange kind
+    const size_t cta = (size_t)std::max(G, 128);
+    const size_t smem_f = 2 * sf.pat.pub_slot.size() * cta * (size_t)tbytes;
+    const size_t smem_a = c.joint ? 2 * (sa.pat.pub_slot.size() + sa.pat.ppub_slot.size()) * cta * (size_t)tbytes : 0;
+    if (std::max(smem_f, smem_a) > 40 * 1024) { rep.why = "halo exchange would need more than 40 KB of shared memory"; return false; }
+  }
   // a lane that reads more operands from other lanes than it owns is a dense coupling: the exchange would dominate, and
   // the dense-operator path (tensor-core GEMM per stage) is the one built for it
   if (rep.halo_fwd > std::max(24, 2 * fa.R) || (c.joint && rep.halo_adj + rep.halo_p > std::max(24, 2 * aa.R))) {

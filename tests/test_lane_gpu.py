@@ -205,3 +205,17 @@ def test_lane_groups_hbm_sized_schedule_is_bit_identical(prec):
     assert part.shape == lit["gradient"].shape and np.all(np.isfinite(part)) and not np.array_equal(part, lit["gradient"])
     o = run_case(_oracle(prec, "reference"), case, want_traj=False)
     assert close(part, np.asarray(o["_p"].getGradient(20)), case["jacobians"][0]["n"], prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec,G", [("f64", 256), ("f32", 128)])
+def test_thousand_dof_chain_on_wide_groups(prec, G):
+    """1000-DOF chain (2002 states -- beyond the shared-memory tile kernels' 1024 rows): in fp64 the group is wider than
+    the default CTA, so the kernels are compiled for a CTA of 256 threads with one barrier per exchange"""
+    case = chain_case(1000, False, E=3, L=200)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("lane_classes") >= 2 and a["_p"]._query("lane_G") == G
+    n, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
