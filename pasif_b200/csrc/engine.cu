@@ -410,6 +410,8 @@ struct pasif_engine {
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
   int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
+  bool aot_on = true;                            // use the prebuilt kernels when a pattern matches (off: always specialise at run time)
+  int jit_minb_fwd = 0, jit_minb_bwd = 0;        // one-thread kernels specialised at run time: minimum CTAs per SM (0: none)
   int lane_minb_fwd = 0, lane_minb_bwd = 0;      // lane-block kernels: minimum CTAs per SM handed to __launch_bounds__ (0: none)
   int one_thread_regs = 330;                     // register estimate above which a component is offered to the lane-block split
   int lane_regs = 240;                           // register estimate a lane pattern may reach before a wider group is tried
@@ -528,6 +530,7 @@ std::vector<char> jit_compile(pasif_engine& E, const std::string& src) {
 void resolve_kernels(pasif_engine& E, DevClass& dc) {
   const ClassData& c = dc.h;
   for (const AotEntry& a : aot_table()) {
+    if (!E.aot_on) break;
     if (a.hash == c.hash && a.joint == c.joint) {
       const void* const* f = E.dtype == PASIF_F32 ? a.f32 : a.f64;
       dc.k_fwd.aot = f[0]; dc.k_gfwd.aot = f[1]; dc.k_bwd.aot = f[2];
@@ -543,7 +546,7 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
                              std::to_string(c.fwd.nc() + c.adj.nc()) + " coefficients: beyond the register-resident "
                              "kernel's range (<= 48 variables); the shared-memory large-system path is not built yet");
   g_drv.load();
-  std::vector<char> cubin = jit_compile(E, jit_source(c, E.dtype, c.lanes > 1 ? E.lane_minb_fwd : 0, c.lanes > 1 ? E.lane_minb_bwd : 0));
+  std::vector<char> cubin = jit_compile(E, jit_source(c, E.dtype, c.lanes > 1 ? E.lane_minb_fwd : E.jit_minb_fwd, c.lanes > 1 ? E.lane_minb_bwd : E.jit_minb_bwd));
   if (g_drv.ModuleLoadData(&dc.module, cubin.data()) != CUDA_SUCCESS)
     throw std::runtime_error("cuModuleLoadData failed for the specialised kernel of " + c.name);
   auto getf = [&](const char* n, CUfunction* f) {
@@ -1251,6 +1254,12 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
     e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 1024 : std::atoi(v.c_str()));
+  } else if (k == "aot") {
+    e->aot_on = (v == "on" || v == "1");
+  } else if (k == "jit_minb_fwd") {
+    e->jit_minb_fwd = std::atoi(v.c_str());
+  } else if (k == "jit_minb_bwd") {
+    e->jit_minb_bwd = std::atoi(v.c_str());
   } else if (k == "lane_minb_fwd") {
     e->lane_minb_fwd = std::atoi(v.c_str());
   } else if (k == "lane_minb_bwd") {
