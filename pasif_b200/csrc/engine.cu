@@ -414,8 +414,9 @@ struct pasif_engine {
   int jit_minb_fwd = 0, jit_minb_bwd = 0;        // one-thread kernels specialised at run time: minimum CTAs per SM (0: none)
   int lane_minb_fwd = 0, lane_minb_bwd = 0;      // lane-block kernels: minimum CTAs per SM handed to __launch_bounds__ (0: none)
   int one_thread_regs = 330;                     // register estimate above which a component is offered to the lane-block split
+  double lane_min_eff = 0.30;                    // smallest share of real terms in the common lane pattern that is accepted
   int lane_regs = 240;                           // register estimate a lane pattern may reach before a wider group is tried
-  long long lane_classes = 0;
+  long long lane_classes = 0, lane_selfcheck_failures = 0;
   LaneSplitReport lane_report;                   // of the last class that was split
   std::string lane_reject;                       // why the last large class was not split
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
@@ -630,7 +631,14 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
       // (dense operators, irregular coupling) stay with the tile kernels / the dense-operator path below
       ClassData split;
       LaneSplitReport rep;
-      if (lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, split, rep)) {
+      bool ok = false;
+      try {
+        ok = lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, E.lane_min_eff, split, rep);
+      } catch (const std::exception& ex) {       // a split that fails its own check is never used: the other paths take over
+        rep.why = ex.what();
+        ++E.lane_selfcheck_failures;
+      }
+      if (ok) {
         dc.h = std::move(split);
         ++E.lane_classes;
         E.lane_report = rep;
@@ -1266,6 +1274,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->lane_minb_bwd = std::atoi(v.c_str());
   } else if (k == "one_thread_regs") {
     e->one_thread_regs = std::atoi(v.c_str());
+  } else if (k == "lane_min_eff") {
+    e->lane_min_eff = std::atof(v.c_str());
   } else if (k == "lane_regs") {
     e->lane_regs = std::atoi(v.c_str());
   } else if (k == "large_threshold") {
@@ -1348,6 +1358,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "dtype") *value = e->dtype;
   else if (k == "large_classes") *value = (double)e->large_classes;
   else if (k == "lane_classes") *value = (double)e->lane_classes;
+  else if (k == "lane_selfcheck_failures") *value = (double)e->lane_selfcheck_failures;
   else if (k == "lane_G") *value = e->lane_report.G;
   else if (k == "lane_R") *value = e->lane_report.R;
   else if (k == "lane_RA") *value = e->lane_report.RA;

@@ -502,7 +502,7 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   }
   // a lane that reads more operands from other lanes than it owns is a dense coupling: the exchange would dominate, and
   // the dense-operator path (tensor-core GEMM per stage) is the one built for it
-  if (rep.halo_fwd > std::max(24, 2 * fa.R) || (c.joint && rep.halo_adj + rep.halo_p > std::max(24, 2 * aa.R))) {
+  if (min_eff > 0 && (rep.halo_fwd > std::max(24, 2 * fa.R) || (c.joint && rep.halo_adj + rep.halo_p > std::max(24, 2 * aa.R)))) {
     rep.why = "too many halo operands per lane (dense coupling)";
     return false;
   }
@@ -584,11 +584,10 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
 
 // Tries group widths from narrow to wide and both unit orders; keeps the first width that fits the register budget,
 // with the order that gives the smaller common pattern.
-inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, ClassData& out, LaneSplitReport& rep) {
+inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, double min_eff, ClassData& out, LaneSplitReport& rep) {
   const long long terms = (long long)c.fwd.nc() + c.adj.nc();
   const long long rows = (long long)c.fwd.N + c.adj.N;
   if (terms > 64 * rows) { rep.why = "operator too dense for a lane split (" + std::to_string(terms / std::max<long long>(rows, 1)) + " terms per row)"; return false; }
-  const double min_eff = 0.30;
   for (int G = 8; G <= max_lanes; G *= 2) {
     ClassData best;
     LaneSplitReport brep;

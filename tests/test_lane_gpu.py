@@ -219,3 +219,26 @@ def test_thousand_dof_chain_on_wide_groups(prec, G):
     assert close(a["amplitudes"], b["amplitudes"], n, prec, TOL_FWD)
     assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
     assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_irregular_system_forced_through_lane_groups(prec):
+    """a random banded system with long-range couplings, split with the cost model switched off: a poor split (halo operands
+    at arbitrary lane offsets, mostly padding terms) that the kernels must still integrate exactly like the oracle"""
+    from pasif_b200 import adjoint
+    from test_lane_split import _random_system
+    rng = np.random.default_rng(42)
+    s = _random_system(rng, 60, band=2, extra=3)
+    # keep the dynamics tame: damp the linear part
+    kv, kr, kc = s["K"]
+    s["K"] = ([v + (40.0 if r == c else 0.0) for v, r, c in zip(kv, kr, kc)], kr, kc)
+    loss = np.zeros(60); loss[7] = 1.0
+    j = adjoint.build_adjoint(s, loss, [("Lambda", 0), ("Gamma", 1), ("K", 0, 0)])
+    case = dict(systems=[s], jacobians=[j], excitations=wl.random_sine_excitations(5, 300, 16000, seed=3), sample_rate=16000,
+                numsteps=0, interp=None, traj_save_steps=50)
+    a = run_case(capi.engine_class(prec), case, options={"lane_regs": "1000000", "lane_min_eff": "0", "lanes": "8"})
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("lane_classes") >= 2 and a["_p"]._query("lane_halo_fwd") > 8
+    assert close(a["amplitudes"], b["amplitudes"], 60, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], 63, prec, TOL_ADJ)
