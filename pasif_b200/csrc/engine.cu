@@ -410,6 +410,7 @@ struct pasif_engine {
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
   int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
+  bool unit_on = true;                           // register kernels: K terms with coefficient exactly 1 become additions
   bool aot_on = true;                            // use the prebuilt kernels when a pattern matches (off: always specialise at run time)
   int jit_minb_fwd = 0, jit_minb_bwd = 0;        // one-thread kernels specialised at run time: minimum CTAs per SM (0: none)
   int lane_minb_fwd = 0, lane_minb_bwd = 0;      // lane-block kernels: minimum CTAs per SM handed to __launch_bounds__ (0: none)
@@ -644,6 +645,7 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
         E.lane_report = rep;
       } else E.lane_reject = rep.why;
     }
+    if (E.unit_on && (dc.h.lanes > 1 || !is_large(E, dc.h))) mark_unit_terms(dc.h);
     dc.n_traj = (long long)dc.h.n_inst * E.E;
     if (dc.n_traj >= (1ll << 31)) throw std::runtime_error("more than 2^31 trajectories in one class");
     if (E.host_only) continue;
@@ -1262,6 +1264,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->tcgen05_on = (v == "on" || v == "1");
   } else if (k == "lanes") {
     e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 1024 : std::atoi(v.c_str()));
+  } else if (k == "unit_terms") {
+    e->unit_on = (v == "on" || v == "1");
   } else if (k == "aot") {
     e->aot_on = (v == "on" || v == "1");
   } else if (k == "jit_minb_fwd") {

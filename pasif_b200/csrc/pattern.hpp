@@ -52,6 +52,9 @@ struct Pattern {
   // lane-block classes (lane_split.hpp): the component is integrated by `lanes` threads; x-operand indices >= N and
   // p-operand indices >= nv.size() address HALO entries: entry h = published slot pub_slot[hx_pub[h]] (== hx_slot[h]) of
   // lane (lane + hx_delta[h]) mod lanes; likewise hp_* / ppub_slot over the set-point (nv) list of the adjoint side
+  // K terms whose coefficient is exactly 1 for every instance (x' = v of a second-order system in first-order form): the
+  // kernels add the operand instead of multiplying by a register (empty: none)
+  std::vector<int> k_unit;
   int lanes = 1;
   std::vector<int> hx_slot, hx_delta, hx_pub, pub_slot, hp_slot, hp_delta, hp_pub, ppub_slot;
   int nc() const { return (int)(k_row.size() + g_o.size() + l_o.size() + p_o.size() + f_row.size()); }
@@ -69,6 +72,9 @@ struct Pattern {
     put("lo", l_o); put("la", l_a); put("lb", l_b); put("lc", l_c);
     put("po", p_o); put("pa", p_a); put("pb", p_b); put("pc", p_c); put("pd", p_d);
     put("f", f_row);
+    bool any_unit = false;
+    for (int u : k_unit) any_unit = any_unit || u != 0;
+    if (any_unit) put("ku", k_unit);
     if (lanes > 1) {
       s << "G" << lanes << ';';
       put("hxs", hx_slot); put("hxd", hx_delta); put("hps", hp_slot); put("hpd", hp_delta);
@@ -381,6 +387,37 @@ inline std::vector<ClassData> analyze_joint(const SystemData& f, const SystemDat
   return finish(acc);
 }
 
+// ---- unit coefficients: flags the K terms whose value is exactly 1 for every instance of the class (lane classes: for
+// every lane that owns the row; a lane where both the row and the operand are padding slots may take it as 1 as well,
+// padding variables start at 0 and then stay 0).  The flags are part of the class signature (a different kernel).
+inline void mark_unit_side(Pattern& p, const std::vector<double>& coef, const std::vector<int>& varmap, int n_inst, int lanes) {
+  const int nk = (int)p.k_row.size();
+  p.k_unit.assign((size_t)nk, 0);
+  bool any = false;
+  for (int k = 0; k < nk; ++k) {
+    const int row = p.k_row[(size_t)k], col = p.k_col[(size_t)k];
+    if (col >= p.N) continue;                                   // halo operand
+    bool ok = n_inst > 0;
+    for (int j = 0; j < n_inst && ok; ++j) {
+      const double v = coef[(size_t)k * n_inst + j];
+      if (v == 1.0) continue;
+      const bool pad = lanes > 1 && v == 0.0 && varmap[(size_t)row * n_inst + j] < 0 && varmap[(size_t)col * n_inst + j] < 0;
+      if (!pad) ok = false;
+    }
+    if (ok) { p.k_unit[(size_t)k] = 1; any = true; }
+  }
+  if (!any) p.k_unit.clear();
+}
+inline void mark_unit_terms(ClassData& c) {
+  mark_unit_side(c.fwd, c.coef, c.varmap, c.n_inst, c.lanes);
+  if (c.joint) mark_unit_side(c.adj, c.coef_adj, c.varmap_adj, c.n_inst, c.lanes);
+  if (c.fwd.k_unit.empty() && c.adj.k_unit.empty()) return;
+  const std::string sig = c.joint ? std::string(c.lanes > 1 ? "JL|" : "J|") + c.fwd.signature() + "|A|" + c.adj.signature()
+                                  : std::string(c.lanes > 1 ? "FL|" : "F|") + c.fwd.signature();
+  c.hash = fnv1a(sig);
+  c.name = std::string(c.joint ? "J_" : "F_") + detail::hex64(c.hash);
+}
+
 // ---- traits emission (consumed by rk4_kernels.cuh; identical text for the AOT include and the NVRTC source)
 inline void emit_table(std::ostringstream& s, const char* name, const std::vector<int>& v) {
   s << "  PASIF_TAB(" << name;
@@ -402,6 +439,15 @@ inline std::string emit_pattern_struct(const std::string& name, const Pattern& p
     << ", OFF_F = " << nk + ng + nl + np << ", NC = " << nk + ng + nl + np + nf << ";\n";
   emit_table(s, "nv", p.nv);
   emit_table(s, "k_row", p.k_row); emit_table(s, "k_col", p.k_col);
+  {
+    std::vector<int> unit((size_t)nk, 0), first((size_t)nk, 0);
+    for (int k = 0; k < nk; ++k) {
+      unit[(size_t)k] = k < (int)p.k_unit.size() ? p.k_unit[(size_t)k] : 0;
+      first[(size_t)k] = 1;
+      for (int j = 0; j < k; ++j) if (p.k_row[(size_t)j] == p.k_row[(size_t)k]) first[(size_t)k] = 0;
+    }
+    emit_table(s, "k_unit", unit); emit_table(s, "k_first", first);
+  }
   emit_table(s, "g_o", p.g_o); emit_table(s, "g_a", p.g_a); emit_table(s, "g_b", p.g_b);
   emit_table(s, "l_o", p.l_o); emit_table(s, "l_a", p.l_a); emit_table(s, "l_b", p.l_b); emit_table(s, "l_c", p.l_c);
   emit_table(s, "p_o", p.p_o); emit_table(s, "p_a", p.p_a); emit_table(s, "p_b", p.p_b); emit_table(s, "p_c", p.p_c);

@@ -167,7 +167,12 @@ PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::N
 #pragma unroll
   for (int r = 0; r < P::N; ++r) y[r] = T(0);
 #pragma unroll
-  for (int k = 0; k < P::NNZK; ++k) y[P::k_row(k)] = fma(c[P::OFF_K + k], x[P::k_col(k)], y[P::k_row(k)]);
+  for (int k = 0; k < P::NNZK; ++k) {
+    // unit coefficient (x' = v): fma(1, x, y) == y + x and fma(1, x, 0) == x, bit for bit (up to the sign of a zero) -- no
+    // multiply, no coefficient register; the flags fold to constants after unrolling
+    if (P::k_unit(k)) y[P::k_row(k)] = P::k_first(k) ? x[P::k_col(k)] : y[P::k_row(k)] + x[P::k_col(k)];
+    else y[P::k_row(k)] = fma(c[P::OFF_K + k], x[P::k_col(k)], y[P::k_row(k)]);
+  }
 #pragma unroll
   for (int k = 0; k < P::NNZG; ++k)
     y[P::g_o(k)] = fma(c[P::OFF_G + k] * x[P::g_a(k)], p[P::g_b(k)], y[P::g_o(k)]);
