@@ -99,7 +99,8 @@ int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t c
 int pasif_fma_peak(int device, int dtype, double* tflops);
 /* isolated check of the dense-operator path's GEMM kernels (no reference counterpart: replaces the cusparseSpMM of
  * src/__GpuDriver.cu:795-807 for a dense shared K'): y[p][m] = sum_k kd[m][k] * x[p][k], kd [n][n], x / y [n_traj][n], row-major doubles.
- * mode 0: mma.sync kernel of the dtype (fp64 DMMA, fp32 3xTF32); mode 1: tcgen05 3xTF32 (fp32 only) */
+ * mode 0: mma.sync kernel of the dtype (fp64 DMMA, fp32 3xTF32); mode 1: tcgen05 3xTF32 with pre-split operands (fp32 only);
+ * mode 2: tcgen05 3xTF32 that splits the fp32 operand in shared memory (fp32 only) */
 int pasif_debug_gemm(int device, int dtype, int mode, uint32_t n, uint64_t n_traj, const double* kd, const double* x, double* y);
 
 #ifdef __cplusplus

@@ -179,4 +179,145 @@ __global__ void __launch_bounds__(128, 1) sgemm_tn_3xtf32_tcgen05_kernel(const _
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ fused hi / lo split
+// Same GEMM, but the trajectory operand arrives as ONE fp32 array: the tile is loaded raw by TMA and split into its tf32
+// hi / lo parts in shared memory, in place, by the four warps that later run the epilogue (they are idle during the main
+// loop).  The update kernel then writes one stage vector instead of three and the GEMM reads 4 instead of 8 bytes per
+// element of X.  192 threads: warps 0-3 convert + epilogue, warp 4 lane 0 TMA producer, warp 5 lane 0 MMA issuer.
+//   full[s]  TMA bytes landed            -> converters
+//   conv[s]  128 converter arrivals      -> MMA issuer   (fence.proxy.async: generic-proxy writes visible to the tensor core)
+//   empty[s] tcgen05.commit              -> producer
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ float tf32_rna(float x) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(x));
+  return __uint_as_float(u);
+}
+
+template <int TC_BN>
+__global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                               const __grid_constant__ CUtensorMap mapBh,
+                                                                               const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y,
+                                                                               int M, int K, int ldy, int p_row0, int m_base, int k_base) {
+  constexpr int TC_STAGES = TcCfg<TC_BN>::STAGES, TC_B_BYTES = TcCfg<TC_BN>::B_BYTES, TC_STAGE_BYTES = TcCfg<TC_BN>::STAGE_BYTES,
+                TC_TMEM_COLS = TcCfg<TC_BN>::TMEM_COLS;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* conv = empty + TC_STAGES;
+  uint64_t* done = conv + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = m_base + blockIdx.x * TC_BN;
+  const int p0 = blockIdx.y * TC_BM;
+  const int nkb = K / TC_BK;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 128); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      // ---- TMA producer: raw X tile + Kd hi / lo tiles
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);
+        unsigned char* st = base + s * TC_STAGE_BYTES;
+        mbar_expect_tx(&full[s], TC_A_BYTES + 2 * TC_B_BYTES);
+        tma_load_2d(st, &mapA, &full[s], k_base + kb * TC_BK, p_row0 + p0);
+        tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], k_base + kb * TC_BK, m0);
+        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], k_base + kb * TC_BK, m0);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      // ---- MMA issuer
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&conv[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(base + s * TC_STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          const uint32_t o = kk * 32;
+          umma_tf32(tmem_d, umma_desc_sw128(a_lo + o), umma_desc_sw128(b_hi + o), idesc, (kb | kk) != 0);
+          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_lo + o), idesc, 1u);
+          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_hi + o), idesc, 1u);
+        }
+        umma_commit(&empty[s]);
+      }
+      umma_commit(done);
+    }
+  } else {
+    // ---- converters (warps 0-3): element-wise, so the 128-byte swizzle of the tile is preserved
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      float4* a = reinterpret_cast<float4*>(base + s * TC_STAGE_BYTES);
+      float4* l = reinterpret_cast<float4*>(base + s * TC_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+      for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+        const int o = threadIdx.x + i * 128;
+        const float4 v = a[o];
+        float4 h, r;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        r.x = tf32_rna(v.x - h.x); r.y = tf32_rna(v.y - h.y); r.z = tf32_rna(v.z - h.z); r.w = tf32_rna(v.w - h.w);
+        a[o] = h;
+        l[o] = r;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&conv[s]);
+    }
+    // ---- epilogue: warp w owns TMEM lanes [32w, 32w + 32)
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* yrow = Y + (size_t)(p0 + warp * 32 + lane) * ldy;
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+          "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int mc = m0 + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (mc + j < M)
+          *reinterpret_cast<float4*>(yrow + mc + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
+}
+
 }  // namespace pasif_tc

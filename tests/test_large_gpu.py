@@ -132,7 +132,8 @@ def test_stage_gemm_kernels_against_numpy(shape):
     ref = x @ kd.T
     scale = np.max(np.abs(ref))
     assert np.max(np.abs(capi.debug_gemm(kd, x, "f64", 0) - ref)) < 1e-13 * scale
-    y_mma, y_tc = capi.debug_gemm(kd, x, "f32", 0), capi.debug_gemm(kd, x, "f32", 1)
+    y_mma, y_tc, y_fs = capi.debug_gemm(kd, x, "f32", 0), capi.debug_gemm(kd, x, "f32", 1), capi.debug_gemm(kd, x, "f32", 2)
     assert np.max(np.abs(y_mma - ref)) < 1e-5 * scale
     assert np.max(np.abs(y_tc - ref)) < 1e-5 * scale
     assert np.max(np.abs(y_tc - y_mma)) < 2e-6 * scale
+    assert np.array_equal(y_fs, y_tc)          # fused in-kernel split: same tf32 halves, same products, same order
