@@ -13,7 +13,7 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpasif_b200.so")
+LIB_PATH = os.environ.get("PASIF_B200_LIB") or os.path.join(HERE, "libpasif_b200.so")   # override: A/B builds of the library
 
 SYMBOLS = """pasif_create pasif_destroy pasif_last_error pasif_load_excitations
 pasif_set_fwd_k pasif_set_fwd_gamma pasif_set_fwd_lambda pasif_set_fwd_psi pasif_set_fwd_force pasif_set_fwd_ic pasif_alloc_system

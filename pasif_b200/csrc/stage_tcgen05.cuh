@@ -16,6 +16,9 @@
 
 namespace pasif_tc {
 
+#ifndef PASIF_TC_STAGES_128
+#define PASIF_TC_STAGES_128 3
+#endif
 constexpr int TC_BM = 128;          // trajectories per tile (UMMA M)
 constexpr int TC_BK = 32;           // floats per k-block (128 bytes)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB (one of hi / lo)
@@ -23,7 +26,7 @@ constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB (one of hi / lo)
 // through the GEMM (256 rows = 2 tiles, no padding work); the narrower tile leaves room for a third pipeline stage
 template <int BN>
 struct TcCfg {
-  static constexpr int STAGES = BN <= 128 ? 3 : 2;
+  static constexpr int STAGES = BN <= 128 ? PASIF_TC_STAGES_128 : 2;
   static constexpr int B_BYTES = BN * TC_BK * 4;        // 24 KB / 16 KB
   static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
