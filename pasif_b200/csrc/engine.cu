@@ -422,6 +422,7 @@ struct pasif_engine {
   std::string lane_reject;                       // why the last large class was not split
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
+  bool tc_multicast = false;                     // fused-split GEMM on clusters of two CTAs with the K' tile multicast (experimental)
   bool tc_fused_split = true;                    // tcgen05 GEMM splits the fp32 stage vector into tf32 hi / lo in shared memory
   bool gemm_band = true;                         // dense-operator path: only the band of dense rows goes through the GEMM
   bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
@@ -1259,6 +1260,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->stage_nparts = n;
   } else if (k == "update_u") {
     e->update_u = std::atoi(v.c_str());
+  } else if (k == "tc_multicast") {
+    e->tc_multicast = (v == "on" || v == "1");
   } else if (k == "tc_split") {
     // "fused": the tcgen05 GEMM splits the stage vector in shared memory; "presplit": the update kernel writes hi / lo copies
     if (v != "fused" && v != "presplit") throw std::runtime_error("tc_split must be 'fused' or 'presplit'");

@@ -323,4 +323,153 @@ __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(c
   if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
 }
 
+// ------------------------------------------------------------------------------------------------ cluster multicast variant
+// The fused-split kernel is bound by what each SM pulls through L2: 16 KB of X and 32 KB of K' per k-block for 3.1 MFLOP.
+// Two CTAs that work on the same rows of K' (neighbouring trajectory tiles) form a cluster (1, 2, 1): each loads HALF of
+// the K' tile (64 rows of hi and of lo) and multicasts it into both shared memories, so every SM pulls 32 KB per k-block.
+// A stage may only be overwritten when BOTH CTAs have consumed it: tcgen05.commit arrives on the `empty` barrier of both
+// CTAs (multicast commit), which therefore counts 2.
+__device__ __forceinline__ void tma_load_2d_mc(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, uint16_t mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;" ::"r"(
+          smem_u32(dst)),
+      "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "h"(mask)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint64_t* bar, uint16_t mask) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
+               : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+// mapBh / mapBl: boxes of TC_BN / 2 rows.  grid.y must be even.
+template <int TC_BN>
+__global__ void __cluster_dims__(1, 2, 1) __launch_bounds__(192, 1)
+    sgemm_tn_3xtf32_tcgen05_split_mc_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapBh,
+                                            const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y, int M, int K, int ldy, int p_row0,
+                                            int m_base, int k_base) {
+  constexpr int TC_STAGES = TcCfg<TC_BN>::STAGES, TC_B_BYTES = TcCfg<TC_BN>::B_BYTES, TC_STAGE_BYTES = TcCfg<TC_BN>::STAGE_BYTES,
+                TC_TMEM_COLS = TcCfg<TC_BN>::TMEM_COLS;
+  extern __shared__ unsigned char tc_smem_raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
+  uint64_t* empty = full + TC_STAGES;
+  uint64_t* conv = empty + TC_STAGES;
+  uint64_t* done = conv + TC_STAGES;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int m0 = m_base + blockIdx.x * TC_BN;
+  const int p0 = blockIdx.y * TC_BM;
+  const int nkb = K / TC_BK;
+  uint32_t rank;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 2); mbar_init(&conv[s], 128); }
+    mbar_init(done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBh) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapBl) : "memory");
+  }
+  if (warp == 2) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(TC_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();                                  // both CTAs' barriers exist before anyone multicasts into them
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  const uint32_t tmem_d = *tmem_slot;
+
+  if (warp == 4) {
+    if (lane == 0) {
+      const int half_rows = TC_BN / 2, half_bytes = TC_B_BYTES / 2;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&empty[s], ph ^ 1);              // both CTAs have consumed this stage
+        unsigned char* st = base + s * TC_STAGE_BYTES;
+        mbar_expect_tx(&full[s], TC_A_BYTES + 2 * TC_B_BYTES);
+        tma_load_2d(st, &mapA, &full[s], k_base + kb * TC_BK, p_row0 + p0);
+        tma_load_2d_mc(st + 2 * TC_A_BYTES + rank * half_bytes, &mapBh, &full[s], k_base + kb * TC_BK, m0 + (int)rank * half_rows, (uint16_t)3);
+        tma_load_2d_mc(st + 2 * TC_A_BYTES + TC_B_BYTES + rank * half_bytes, &mapBl, &full[s], k_base + kb * TC_BK, m0 + (int)rank * half_rows,
+                       (uint16_t)3);
+      }
+    }
+  } else if (warp == 5) {
+    if (lane == 0) {
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int s = kb % TC_STAGES;
+        const uint32_t ph = (kb / TC_STAGES) & 1;
+        mbar_wait(&conv[s], ph);
+        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+        const uint32_t sa = smem_u32(base + s * TC_STAGE_BYTES);
+        const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
+#pragma unroll
+        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+          const uint32_t o = kk * 32;
+          umma_tf32(tmem_d, umma_desc_sw128(a_lo + o), umma_desc_sw128(b_hi + o), idesc, (kb | kk) != 0);
+          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_lo + o), idesc, 1u);
+          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_hi + o), idesc, 1u);
+        }
+        umma_commit_mc(&empty[s], (uint16_t)3);    // this CTA is done with the stage: tell both producers
+      }
+      umma_commit(done);
+    }
+  } else {
+    for (int kb = 0; kb < nkb; ++kb) {
+      const int s = kb % TC_STAGES;
+      const uint32_t ph = (kb / TC_STAGES) & 1;
+      mbar_wait(&full[s], ph);
+      float4* a = reinterpret_cast<float4*>(base + s * TC_STAGE_BYTES);
+      float4* l = reinterpret_cast<float4*>(base + s * TC_STAGE_BYTES + TC_A_BYTES);
+#pragma unroll
+      for (int i = 0; i < TC_A_BYTES / 16 / 128; ++i) {
+        const int o = threadIdx.x + i * 128;
+        const float4 v = a[o];
+        float4 h, r;
+        h.x = tf32_rna(v.x); h.y = tf32_rna(v.y); h.z = tf32_rna(v.z); h.w = tf32_rna(v.w);
+        r.x = tf32_rna(v.x - h.x); r.y = tf32_rna(v.y - h.y); r.z = tf32_rna(v.z - h.z); r.w = tf32_rna(v.w - h.w);
+        a[o] = h;
+        l[o] = r;
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      mbar_arrive(&conv[s]);
+    }
+    mbar_wait(done, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    float* yrow = Y + (size_t)(p0 + warp * 32 + lane) * ldy;
+#pragma unroll 1
+    for (int c = 0; c < TC_BN / 32; ++c) {
+      uint32_t v[32];
+      const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
+      asm volatile(
+          "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
+          "%21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+          : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]),
+            "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]),
+            "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
+            "=r"(v[31])
+          : "r"(taddr));
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      const int mc = m0 + c * 32;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        if (mc + j < M)
+          *reinterpret_cast<float4*>(yrow + mc + j) =
+              make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]), __uint_as_float(v[j + 3]));
+      }
+    }
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  cluster_sync();                                  // the peer may still multicast into this CTA / arrive on its barriers
+  if (warp == 2) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_d), "r"(TC_TMEM_COLS) : "memory");
+}
+
 }  // namespace pasif_tc
