@@ -1260,6 +1260,16 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->stage_nparts = n;
   } else if (k == "update_u") {
     e->update_u = std::atoi(v.c_str());
+  } else if (k == "bwd_priority") {
+    // scheduling priority of the adjoint stream against the recompute stream: "high" | "low" | "default"
+    if (e->host_only) return 0;
+    CUDA_CHECK(cudaSetDevice(e->device));
+    int lo = 0, hi = 0;
+    CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));      // lo = least priority (numerically greatest)
+    if (e->stream2) { CUDA_CHECK(cudaStreamSynchronize(e->stream2)); CUDA_CHECK(cudaStreamDestroy(e->stream2)); e->stream2 = nullptr; }
+    if (v == "high") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi));
+    else if (v == "low") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, lo));
+    else CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   } else if (k == "tc_multicast") {
     e->tc_multicast = (v == "on" || v == "1");
   } else if (k == "tc_split") {
