@@ -36,6 +36,7 @@ struct UpdArgs {
   T* Xn;                 // [P][NR] next stage vector (stage 4: the new state)
   T* Xn_hi;              // fp32 only: tf32 split of Xn for the next 3xTF32 GEMM
   T* Xn_lo;
+  T* Qsave;              // stage 4: second copy of the new state (a chunk-trajectory slot of the adjoint recompute), or nullptr
   const T* fe;           // excitation samples of this stage [E] (nullptr: unforced)
   int stage;             // 1..4
   int E, n_traj;         // n_traj: trajectories of THIS launch (a contiguous part of the batch)
@@ -46,99 +47,139 @@ struct UpdArgs {
 // grid (ceil(n_traj / (U * UPD_TG)), NR / 32), block (32, UPD_TG): a warp = 32 consecutive rows of U trajectories
 constexpr int UPD_TG = 8;
 
-// the kernel is HBM-bound: registers are capped at 64 so that 4 CTAs of 256 threads stay resident per SM (measured: fp32 +7 %, fp64 +3 %; a tighter cap spills)
-template <typename T, int U>
-__global__ void __launch_bounds__(32 * UPD_TG, 4) stage_update_kernel(const UpdArgs<T> a) {
+// Body of the update for the U trajectories of one thread.  STAGE and HALF (adjoint half stage: set point = mean of two
+// forward states) are compile-time, so the stage arithmetic and the set-point fetch carry no branches.  UNI (chosen by
+// the host: U divides E and the part's first trajectory): the U trajectories of a thread always belong to ONE instance
+// -- a coefficient is then fetched once per term instead of once per trajectory, and rows past the batch need no clamp
+// (they map to valid excitations of the same instance).  Offsets inside the thread's block of U rows are 32-bit; only the
+// block's base pointers are 64-bit (ncu of the first version: 74 % of the issue slots busy, 2/3 of them 64-bit address
+// arithmetic and four 64-bit divisions per thread; DRAM at 43 %).
+template <typename T, int U, int STAGE, bool HALF, bool UNI>
+__device__ __forceinline__ void stage_update_body(const UpdArgs<T>& a, const int r, const long long p0, const unsigned inst0, const unsigned e0) {
   const Tables& tb = a.tb;
   const int NR = tb.NR, NPR = tb.NPR;
-  const int r = blockIdx.y * 32 + threadIdx.x;
-  const long long p0 = ((long long)blockIdx.x * UPD_TG + threadIdx.y) * U;
-  if (p0 >= a.n_traj) return;
   const int4 w = __ldg(tb.widths + (r >> 5));
-  const T* X = a.X + p0 * NR;
-  const T* Pa = a.Pa + p0 * NPR;
-  const T* Pb = a.Pb ? a.Pb + p0 * NPR : nullptr;
+  const T* __restrict__ X = a.X + p0 * NR;
+  const T* __restrict__ Pa = a.Pa + p0 * NPR;
+  const T* __restrict__ Pb = HALF ? a.Pb + p0 * NPR : nullptr;
+  const size_t o0 = (size_t)p0 * NR + r;
+  const T* __restrict__ Yr = a.Y + o0;
+  T* __restrict__ Qr = a.Q + o0;
+  T* __restrict__ Sr = a.S + o0;
   T y[U], q[U], sv[U];
-  int inst[U];
+  unsigned ib[U], eb[U];                    // instance / excitation of trajectory b (general path)
+  const bool in_band = r >= a.y_lo && r < a.y_hi;
   // every HBM operand of the row is requested up front (Y, Q, S of U trajectories: 3 U independent loads in flight per
-  // thread) -- the kernel is bandwidth-bound and the row programs below only gather from the L1/L2-resident stage vector
+  // thread); the row programs below only gather from the L1/L2-resident stage vector.  Arrays are padded to a multiple
+  // of 128 trajectories, so rows past n_traj are readable (they recompute the last trajectory's coefficients).
 #pragma unroll
   for (int b = 0; b < U; ++b) {
-    const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;      // clamp: lanes past the batch recompute the last one
-    inst[b] = (int)((a.p_base + p) / a.E);
-    const long long o = (p0 + b) * NR + r;                               // arrays are padded to a multiple of U rows
-    y[b] = (r >= a.y_lo && r < a.y_hi) ? a.Y[o] : T(0);
-    q[b] = a.Q[o];
-    sv[b] = a.stage >= 2 ? a.S[o] : T(0);
+    y[b] = in_band ? Yr[b * NR] : T(0);
+    q[b] = Qr[b * NR];
+    sv[b] = STAGE >= 2 ? Sr[b * NR] : T(0);
   }
-  auto P = [&](int b, int c) -> T {
-    const T v = Pa[(long long)b * NPR + c];
-    return Pb ? T(.5) * (v + Pb[(long long)b * NPR + c]) : v;
-  };
+  if constexpr (!UNI) {
+    const unsigned E = (unsigned)a.E;
+    const long long last = a.n_traj - 1 - p0;                      // >= 0
+    unsigned i = inst0, e = e0;
+#pragma unroll
+    for (int b = 0; b < U; ++b) {
+      ib[b] = i; eb[b] = e;
+      if (b < last) { if (++e == E) { e = 0; ++i; } }              // lanes past the batch stay on the last trajectory
+    }
+  }
   const size_t cs = (size_t)tb.coef_stride;
-  const T* v0 = a.vals + r;
+  const T* __restrict__ v0 = a.vals + r;
+  const T* __restrict__ vu = v0 + inst0 * cs;
+  auto coef = [&](int b, int o) -> T { return UNI ? T(0) : __ldg(v0 + ib[b] * cs + o); };
+  auto P = [&](int b, int c) -> T {
+    const T v = Pa[b * NPR + c];
+    if constexpr (HALF) return T(.5) * (v + Pb[b * NPR + c]);
+    else return v;
+  };
   // sparse rows (x' = v, probes ...): their few linear terms as a row program, in CSR order like the reference
+  // (trip counts are 0-3: the loops stay rolled)
+  int off = 0;
+#pragma unroll 1
   for (int j = 0; j < w.x; ++j) {
     const int col = __ldg(tb.k_col + j * NR + r);
+    const T cu = UNI ? __ldg(vu + off + j * NR) : T(0);
 #pragma unroll
     for (int b = 0; b < U; ++b) {
-      const T kv = __ldg(v0 + inst[b] * cs + (size_t)j * NR);
-      y[b] = fma(kv, X[(long long)b * NR + col], y[b]);
+      const T kv = UNI ? cu : coef(b, off + j * NR);
+      y[b] = fma(kv, X[b * NR + col], y[b]);
     }
   }
-  size_t off = (size_t)tb.WK * NR;
+  off += tb.WK * NR;
+#pragma unroll 1
   for (int j = 0; j < w.y; ++j) {
     const int2 ix = __ldg(tb.g_idx + j * NR + r);
+    const T cu = UNI ? __ldg(vu + off + j * NR) : T(0);
 #pragma unroll
     for (int b = 0; b < U; ++b) {
-      const T gv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
-      y[b] = fma(gv * X[(long long)b * NR + ix.x], P(b, ix.y), y[b]);
+      const T gv = UNI ? cu : coef(b, off + j * NR);
+      y[b] = fma(gv * X[b * NR + ix.x], P(b, ix.y), y[b]);
     }
   }
-  off += (size_t)tb.WG * NR;
+  off += tb.WG * NR;
+#pragma unroll 1
   for (int j = 0; j < w.z; ++j) {
     const int4 ix = __ldg(tb.l_idx + j * NR + r);
+    const T cu = UNI ? __ldg(vu + off + j * NR) : T(0);
 #pragma unroll
     for (int b = 0; b < U; ++b) {
-      const T lv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
-      y[b] = fma(lv * X[(long long)b * NR + ix.x] * P(b, ix.y), P(b, ix.z), y[b]);
+      const T lv = UNI ? cu : coef(b, off + j * NR);
+      y[b] = fma(lv * X[b * NR + ix.x] * P(b, ix.y), P(b, ix.z), y[b]);
     }
   }
-  off += (size_t)tb.WL * NR;
+  off += tb.WL * NR;
+#pragma unroll 1
   for (int j = 0; j < w.w; ++j) {
     const int4 ix = __ldg(tb.p_idx + j * NR + r);
+    const T cu = UNI ? __ldg(vu + off + j * NR) : T(0);
 #pragma unroll
     for (int b = 0; b < U; ++b) {
-      const T pv = __ldg(v0 + inst[b] * cs + off + (size_t)j * NR);
-      y[b] = fma(pv * X[(long long)b * NR + ix.x] * P(b, ix.y) * P(b, ix.z), P(b, ix.w), y[b]);
+      const T pv = UNI ? cu : coef(b, off + j * NR);
+      y[b] = fma(pv * X[b * NR + ix.x] * P(b, ix.y) * P(b, ix.z), P(b, ix.w), y[b]);
     }
   }
-  off += (size_t)tb.WP * NR;
+  off += tb.WP * NR;
   if (a.fe) {
+    const T cu = UNI ? __ldg(vu + off) : T(0);
 #pragma unroll
     for (int b = 0; b < U; ++b) {
-      const long long p = p0 + b < a.n_traj ? p0 + b : a.n_traj - 1;
-      const T fr = __ldg(v0 + inst[b] * cs + off);
-      y[b] = fma(fr, __ldg(a.fe + (int)(a.p_base + p - (long long)inst[b] * a.E)), y[b]);
+      const T fr = UNI ? cu : coef(b, off);
+      y[b] = fma(fr, __ldg(a.fe + (UNI ? e0 + b : eb[b])), y[b]);
     }
   }
+  T* __restrict__ Xn = a.Xn + o0;
 #pragma unroll
   for (int b = 0; b < U; ++b) {
-    const long long o = (p0 + b) * NR + r;
     T xn;
-    if (a.stage == 1) { a.S[o] = y[b]; xn = fma(a.h2, y[b], q[b]); }
-    else if (a.stage == 2) { a.S[o] = fma(T(2), y[b], sv[b]); xn = fma(a.h2, y[b], q[b]); }
-    else if (a.stage == 3) { a.S[o] = fma(T(2), y[b], sv[b]); xn = fma(a.h, y[b], q[b]); }
-    else { xn = fma(a.h6, sv[b] + y[b], q[b]); a.Q[o] = xn; }
-    a.Xn[o] = xn;
+    if constexpr (STAGE == 1) { Sr[b * NR] = y[b]; xn = fma(a.h2, y[b], q[b]); }
+    else if constexpr (STAGE == 2) { Sr[b * NR] = fma(T(2), y[b], sv[b]); xn = fma(a.h2, y[b], q[b]); }
+    else if constexpr (STAGE == 3) { Sr[b * NR] = fma(T(2), y[b], sv[b]); xn = fma(a.h, y[b], q[b]); }
+    else { xn = fma(a.h6, sv[b] + y[b], q[b]); Qr[b * NR] = xn; if (a.Qsave) a.Qsave[o0 + b * NR] = xn; }
+    Xn[b * NR] = xn;
     if constexpr (sizeof(T) == 4) {
       if (a.Xn_hi) {
         const float hi = __uint_as_float(pasif_large::f2tf32(xn));
-        a.Xn_hi[o] = hi;
-        a.Xn_lo[o] = __uint_as_float(pasif_large::f2tf32(xn - hi));
+        a.Xn_hi[o0 + b * NR] = hi;
+        a.Xn_lo[o0 + b * NR] = __uint_as_float(pasif_large::f2tf32(xn - hi));
       }
     }
   }
+}
+
+// the kernel is HBM-bound: registers are capped at 64 so that 4 CTAs of 256 threads stay resident per SM (measured: fp32 +7 %, fp64 +3 %; a tighter cap spills)
+template <typename T, int U, int STAGE, bool HALF, bool UNI>
+__global__ void __launch_bounds__(32 * UPD_TG, 4) stage_update_kernel(const UpdArgs<T> a) {
+  const int r = blockIdx.y * 32 + threadIdx.x;
+  const long long p0 = ((long long)blockIdx.x * UPD_TG + threadIdx.y) * U;
+  if (p0 >= a.n_traj) return;
+  const unsigned pg0 = (unsigned)(a.p_base + p0);                  // the host refuses classes of 2^31 trajectories or more
+  const unsigned inst0 = pg0 / (unsigned)a.E, e0 = pg0 - inst0 * (unsigned)a.E;
+  stage_update_body<T, U, STAGE, HALF, UNI>(a, r, p0, inst0, e0);
 }
 
 // state initialisation: Q = X = ic (per instance), optional tf32 split
