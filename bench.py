@@ -364,6 +364,8 @@ def main():
     # launch; the recompute and adjoint kernels are serialised for this pass, they overlap on two streams above)
     k_ms = {"gfwd": 0.0, "bwd": 0.0}
     k_launch = {"gfwd": 0, "bwd": 0}
+    u_ms = {"upd_fwd": 0.0, "upd_adj": 0.0}          # dense-operator path only: its fused update kernels
+    u_launch = {"upd_fwd": 0, "upd_adj": 0}
     p._setOption("profile", "on")
     serial_ms = 0.0
     for _ in range(a.steps):
@@ -372,6 +374,9 @@ def main():
         for k in k_ms:
             k_ms[k] += p._query("ms_" + k)
             k_launch[k] += int(p._query("launches_" + k))
+        for k in u_ms:
+            u_ms[k] += p._query("ms_" + k)
+            u_launch[k] += int(p._query("launches_" + k))
     p._setOption("profile", "off")
     barrier()
     # ---------------- K forward-only passes (RK4 system-steps/s)
@@ -477,6 +482,32 @@ def main():
     # chunk-trajectory traffic: needed forward variables written once (recompute) and read once (adjoint)
     hbm_bytes = pairs * steps_bwd * 2 * N_NEEDED * sz + pairs * nsp * (N_NEEDED if large else N_FWD) * sz * 2
     hbm_peak = peaks.get("hbm_gbs", 6650.0)
+    hbm_note = "algorithmic chunk-trajectory + checkpoint bytes of the whole gradient step over its device time"
+    stage_hbm = None
+    if stage:
+        # dense-operator path: the state lives in HBM between the stages.  Algorithmic values moved per trajectory and
+        # RK4 stage (averaged over the four stages): the GEMM reads the stage vector (band columns) and writes Y (band
+        # rows); the update reads Y (band rows), Q, S (stages 2-4), the stage vector (row-program operands; just read by
+        # the GEMM, so partly L2 hits) and, in the adjoint, the forward set point (twice on the half stages); it writes
+        # S (stages 1-3), the next stage vector and, in stage 4, Q (+ the chunk-trajectory slot while recomputing).
+        q = lambda k: p._query("stage_band_" + k)
+        nrf, nra = q("nr_fwd"), q("nr_adj")
+        upd_f = q("rows_fwd") + (1 + .75 + 1 + .75 + 1 + .25) * nrf
+        upd_a = q("rows_adj") + (1 + .75 + 1 + .75 + 1 + .25) * nra + 1.5 * nrf
+        gemm_f, gemm_a = q("cols_fwd") + q("rows_fwd"), q("cols_adj") + q("rows_adj")
+        stages_f, stages_a = 4 * steps_gfwd, 4 * steps_bwd
+        hbm_bytes = pairs * sz * (stages_f * (upd_f + gemm_f) + (steps_gfwd - L) * nrf + stages_a * (upd_a + gemm_a))
+        hbm_note = ("dense-operator path: algorithmic stage-vector bytes (GEMM operand / result + the update kernel's Y, Q, S, "
+                    "stage vector, set point) of the whole gradient step over its device time")
+        ppad_u = (pairs + 31) // 32 * 32
+        stage_hbm = {}
+        for k, vals in (("upd_fwd", upd_f), ("upd_adj", upd_a)):
+            if u_launch[k]:
+                us = u_ms[k] / u_launch[k] * 1e3
+                gbs = pairs * vals * sz / (us * 1e-6) / 1e9
+                stage_hbm[k] = {"kernel": "stage_update_kernel", "us_per_launch": us, "launches_per_step": u_launch[k] // a.steps,
+                                "ms_per_step": u_ms[k] / a.steps, "algorithmic_bytes_per_launch": pairs * vals * sz,
+                                "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
     line = {
         "metric": "fwd+adjoint gradient evals/s", "value": value, "unit": "gradient evals/s", "n_gpus": world,
         "steps": a.steps, "warmup": max(a.warmup, 3), "ms_per_step": dev_ms / a.steps, "higher_is_better": True,
@@ -503,7 +534,7 @@ def main():
                      "note": "per-kernel figures from a serialised pass (profile=on); value/whole_step from the two-stream overlapped schedule"},
         "roofline_hbm": {"bound": "hbm", "achieved": hbm_bytes / (dev_ms / a.steps * 1e-3) / 1e9, "peak": hbm_peak,
                          "unit": "GB/s", "frac": hbm_bytes / (dev_ms / a.steps * 1e-3) / 1e9 / hbm_peak,
-                         "note": "algorithmic chunk-trajectory + checkpoint bytes of the whole gradient step over its device time",
+                         "note": hbm_note,
                          "peak_source": "MEASURED_PEAKS.json" if peaks else "fallback"},
         "e2e": {"value": e2e_value, "unit": "gradient evals/s", "h2d_bytes_per_step": int(exc.nbytes),
                 "d2h_bytes_per_step": int(pairs * N_ADJ * sz), "host_buffers": "pageable numpy arrays through the C ABI, staged through two pinned slots inside the engine",
@@ -520,6 +551,8 @@ def main():
         line["config"]["path"] = "lane-block register kernels (lane_split.hpp): G threads per trajectory, state in registers, halo exchange per stage"
     elif large:
         line["config"]["path"] = "dense-operator stage path (tensor-core GEMM per stage)" if stage else "shared-memory tile kernels"
+    if stage_hbm:
+        line["roofline_hbm"]["update_kernels"] = stage_hbm
     if tensor is not None:
         line["roofline_fma"] = line["roofline"]
         line["roofline"] = tensor

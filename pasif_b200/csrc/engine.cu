@@ -434,8 +434,10 @@ struct pasif_engine {
   std::vector<cudaEvent_t> prof_events;
   std::vector<int> prof_kinds;
   size_t prof_used = 0;
-  double kind_ms[3] = {0, 0, 0};
-  long long kind_launches[3] = {0, 0, 0};
+  // profile=on: device time per kernel kind (0 forward, 1 gradient sweep / recompute, 2 adjoint; dense-operator path: those
+  // are its GEMMs, and 3 / 4 its update kernels of the forward system / of the adjoint)
+  double kind_ms[5] = {0, 0, 0, 0, 0};
+  long long kind_launches[5] = {0, 0, 0, 0, 0};
 
   size_t tsize() const { return dtype == PASIF_F32 ? 4 : 8; }
   void use_device() {
@@ -733,7 +735,7 @@ void begin_timing(pasif_engine& E) {
   E.last_launches = 0;
   E.prof_used = 0;
   E.prof_kinds.clear();
-  for (int k = 0; k < 3; ++k) { E.kind_ms[k] = 0; E.kind_launches[k] = 0; }
+  for (int k = 0; k < 5; ++k) { E.kind_ms[k] = 0; E.kind_launches[k] = 0; }
   CUDA_CHECK(cudaEventRecord(E.ev0, E.stream));
 }
 void end_timing(pasif_engine& E) {
@@ -1397,7 +1399,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
   else if (k.rfind("stage_band_", 0) == 0) {
     // rows / columns of K' that go through the per-stage GEMM of the (first) dense-operator class:
-    // stage_band_rows_fwd | stage_band_rows_adj | stage_band_cols_fwd | stage_band_cols_adj
+    // stage_band_rows_fwd | stage_band_rows_adj | stage_band_cols_fwd | stage_band_cols_adj; stage_band_nr_fwd | _adj:
+    // padded rows of the state arrays
     *value = 0;
     const bool fwd = k.size() > 4 && k.compare(k.size() - 4, 4, "_fwd") == 0;
     const bool rows = k.find("_rows_") != std::string::npos;
@@ -1405,7 +1408,8 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
       for (auto& c : *v)
         if (*value == 0 && c.large && c.large->stage) {
           const LargeSide& sd = fwd ? c.large->fwd : c.large->adj;
-          *value = rows ? (double)(sd.band_hi - sd.band_lo) : (double)(sd.kband_hi - sd.kband_lo);
+          if (k.find("_nr_") != std::string::npos) *value = (double)sd.tb.NR;
+          else *value = rows ? (double)(sd.band_hi - sd.band_lo) : (double)(sd.kband_hi - sd.kband_lo);
         }
   }
   else if (k == "aot_table_size") *value = (double)aot_table().size();
@@ -1415,6 +1419,10 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "launches_fwd") *value = (double)e->kind_launches[0];
   else if (k == "launches_gfwd") *value = (double)e->kind_launches[1];
   else if (k == "launches_bwd") *value = (double)e->kind_launches[2];
+  else if (k == "ms_upd_fwd") *value = e->kind_ms[3];
+  else if (k == "ms_upd_adj") *value = e->kind_ms[4];
+  else if (k == "launches_upd_fwd") *value = (double)e->kind_launches[3];
+  else if (k == "launches_upd_adj") *value = (double)e->kind_launches[4];
   else return 2;
   return 0;
 }
