@@ -423,6 +423,7 @@ struct pasif_engine {
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
   bool tc_multicast = false;                     // fused-split GEMM on clusters of two CTAs with the K' tile multicast (experimental)
+  int tc_bn = 256;                               // fused-split GEMM: 256-row tiles when the band of dense rows is a multiple of 256 (else 128 / 192)
   bool tc_fused_split = true;                    // tcgen05 GEMM splits the fp32 stage vector into tf32 hi / lo in shared memory
   bool gemm_band = true;                         // dense-operator path: only the band of dense rows goes through the GEMM
   bool gemm_stage = true;                        // dense shared K: per-stage batched GEMM with HBM-resident state (else in-tile GEMM)
@@ -1272,6 +1273,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     if (v == "high") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi));
     else if (v == "low") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, lo));
     else CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  } else if (k == "tc_bn") {
+    e->tc_bn = std::atoi(v.c_str());
   } else if (k == "tc_multicast") {
     e->tc_multicast = (v == "on" || v == "1");
   } else if (k == "tc_split") {

@@ -137,3 +137,33 @@ def test_stage_gemm_kernels_against_numpy(shape):
     assert np.max(np.abs(y_tc - ref)) < 1e-5 * scale
     assert np.max(np.abs(y_tc - y_mma)) < 2e-6 * scale
     assert np.array_equal(y_fs, y_tc)          # fused in-kernel split: same tf32 halves, same products, same order
+
+
+@pytest.mark.parametrize("shape", [(256, 300), (512, 1024)])
+def test_wide_tile_gemm_is_bit_identical(shape):
+    """256-row tiles of the fused-split tcgen05 GEMM (the default when the band of dense rows is a multiple of 256, as in
+    BASELINE config 4): same products in the same order as the 128-row tiles."""
+    N, P = shape
+    rng = np.random.default_rng(N + P)
+    kd, x = rng.standard_normal((N, N)), rng.standard_normal((P, N))
+    ref = x @ kd.T
+    y_fs, y_wide = capi.debug_gemm(kd, x, "f32", 2), capi.debug_gemm(kd, x, "f32", 4)
+    assert np.max(np.abs(y_wide - ref)) < 1e-5 * np.max(np.abs(ref))
+    assert np.array_equal(y_fs, y_wide)
+
+
+def test_config4_size_dense_chain_matches_oracle_f32():
+    """The 256-DOF dense chain of BASELINE config 4 (514 states, band of 256 dense rows -> 256-row GEMM tiles) on a few
+    excitations: forward and gradient against the oracle, and bit-identical to the 128-row tiles (tc_bn=128)."""
+    case = chain_case(256, True, E=12, L=24)
+    a = run_case(capi.engine_class("f32"), case)
+    n = run_case(capi.engine_class("f32"), case, options={"tc_bn": "128"})
+    b = run_case(_oracle("f32", "reference"), case)
+    assert a["_p"]._query("large_stage_classes") >= 1
+    assert a["_p"]._query("stage_band_rows_fwd") == 256
+    nf, na = case["systems"][0]["n"], case["jacobians"][0]["n"]
+    for key in ("amplitudes", "trajectory", "gradient"):
+        assert np.array_equal(a[key], n[key]), key
+    assert close(a["amplitudes"], b["amplitudes"], nf, "f32", TOL_FWD)
+    assert close(a["gradient"], b["gradient"], na, "f32", TOL_ADJ)
+
