@@ -33,6 +33,8 @@ struct Tables {
   const int4* p_idx;     // [WP][NR]  (a, b, c, d)
   const int4* widths;    // [NR/32]   per-warp slot counts (wk, wg, wl, wp): loops are warp-uniform
   int coef_stride;       // values per instance = (WK + WG + WL + WP + 1) * NR   (last slot: force pattern F')
+  int flags;             // dense-operator update kernel: operand indices that coincide in EVERY entry of a table, so one gather
+                         // serves two operands: 1 Gamma a == b, 2 Lambda a == b, 4 Lambda b == c (on-site x^2 / x^3 terms)
 };
 
 template <typename T>
