@@ -167,3 +167,35 @@ def test_config4_size_dense_chain_matches_oracle_f32():
     assert close(a["amplitudes"], b["amplitudes"], nf, "f32", TOL_FWD)
     assert close(a["gradient"], b["gradient"], na, "f32", TOL_ADJ)
 
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("variant", ["gamma_offsite", "lambda_ab_offsite", "lambda_c_offsite"])
+def test_dense_operator_offsite_nonlinear_terms(variant, prec):
+    """The update kernel of the dense-operator path shares one operand gather between the operands of a term when their
+    indices coincide in EVERY entry of the class (on-site x^2 / x^3).  Here some do not: x_i x_{i+1}, x_i x_{i+1}^2,
+    x_i^2 x_{i+1} couplings clear one flag each, so every combination of the shared / separate gathers is compared with
+    the oracle, forward and adjoint (Jacobian from pasif_b200.adjoint.build_adjoint)."""
+    base = wl.chain_system(40, dense=True, seed=3)
+    n = 40
+    s = dict(base)
+    gd, gv, gi = base["Gamma"]
+    ld, lv, li = base["Lambda"]
+    gi, li = list(gi), list(li)
+    for i in range(n - 1):
+        if variant == "gamma_offsite":
+            gi[3 * (i + 1) + 2] = i + 1                     # [n + i, i, i + 1]   (entry 0 is the probe term)
+        elif variant == "lambda_ab_offsite":
+            li[4 * i + 2], li[4 * i + 3] = i + 1, i + 1     # [n + i, i, i + 1, i + 1]
+        else:
+            li[4 * i + 3] = i + 1                           # [n + i, i, i, i + 1]
+    s["Gamma"], s["Lambda"] = (gd, gv, gi), (ld, lv, li)
+    case = dict(systems=[s], jacobians=[wl.chain_jacobian(s, 3)], excitations=wl.random_sine_excitations(12, 400, 16000, seed=8),
+                sample_rate=16000, numsteps=0, interp=None, traj_save_steps=80)
+    a = run_case(capi.engine_class(prec), case)
+    b = run_case(_oracle(prec, "reference"), case)
+    assert a["_p"]._query("large_stage_classes") >= 1
+    nf, na = s["n"], case["jacobians"][0]["n"]
+    assert close(a["amplitudes"], b["amplitudes"], nf, prec, TOL_FWD)
+    assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
+    assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
+
