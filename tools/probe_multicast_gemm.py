@@ -1,5 +1,5 @@
-import sys
-sys.path.insert(0,'/root/repo')
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 from pasif_b200 import capi
 for N,P in ((128,512),(256,1024),(128,256)):
