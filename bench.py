@@ -492,8 +492,11 @@ def main():
         # S (stages 1-3), the next stage vector and, in stage 4, Q (+ the chunk-trajectory slot while recomputing).
         q = lambda k: p._query("stage_band_" + k)
         nrf, nra = q("nr_fwd"), q("nr_adj")
-        upd_f = q("rows_fwd") + (1 + .75 + 1 + .75 + 1 + .25) * nrf
-        upd_a = q("rows_adj") + (1 + .75 + 1 + .75 + 1 + .25) * nra + 1.5 * nrf
+        # stage_direct (default): stage 1 evaluates at the state array (no separate stage vector to read) and stage 4 writes
+        # the state array only: Q 1 + S .75 + stage vector .75 read; S .75 + stage vector .75 + Q .25 written
+        per_nr = (1 + .75 + .75) + (.75 + .75 + .25) if p._query("stage_direct") else (1 + .75 + 1) + (.75 + 1 + .25)
+        upd_f = q("rows_fwd") + per_nr * nrf
+        upd_a = q("rows_adj") + per_nr * nra + 1.5 * nrf
         gemm_f, gemm_a = q("cols_fwd") + q("rows_fwd"), q("cols_adj") + q("rows_adj")
         stages_f, stages_a = 4 * steps_gfwd, 4 * steps_bwd
         hbm_bytes = pairs * sz * (stages_f * (upd_f + gemm_f) + (steps_gfwd - L) * nrf + stages_a * (upd_a + gemm_a))

@@ -423,6 +423,7 @@ struct pasif_engine {
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
   bool tc_multicast = false;                     // fused-split GEMM on clusters of two CTAs with the K' tile multicast (experimental)
+  bool stage_direct = true;                      // dense-operator path: the state array is the stage vector of stage 1 (stage 4 writes one array)
   int tc_bn = 256;                               // fused-split GEMM: 256-row tiles when the band of dense rows is a multiple of 256 (else 128 / 192)
   bool tc_fused_split = true;                    // tcgen05 GEMM splits the fp32 stage vector into tf32 hi / lo in shared memory
   bool gemm_band = true;                         // dense-operator path: only the band of dense rows goes through the GEMM
@@ -1273,6 +1274,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     if (v == "high") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, hi));
     else if (v == "low") CUDA_CHECK(cudaStreamCreateWithPriority(&e->stream2, cudaStreamNonBlocking, lo));
     else CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
+  } else if (k == "stage_direct") {
+    e->stage_direct = (v == "on" || v == "1");
   } else if (k == "tc_bn") {
     e->tc_bn = std::atoi(v.c_str());
   } else if (k == "tc_multicast") {
@@ -1400,6 +1403,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
+  else if (k == "stage_direct") *value = stage_direct(*e, e->dtype == PASIF_F32 ? 4 : 8) ? 1.0 : 0.0;
   else if (k.rfind("stage_band_", 0) == 0) {
     // rows / columns of K' that go through the per-stage GEMM of the (first) dense-operator class:
     // stage_band_rows_fwd | stage_band_rows_adj | stage_band_cols_fwd | stage_band_cols_adj; stage_band_nr_fwd | _adj:

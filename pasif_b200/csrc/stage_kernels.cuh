@@ -33,7 +33,7 @@ struct UpdArgs {
   const T* Pb;           // adjoint half stage: P = (Pa + Pb) / 2 ; else nullptr
   T* Q;                  // [P][NR] state
   T* S;                  // [P][NR] running stage sum
-  T* Xn;                 // [P][NR] next stage vector (stage 4: the new state)
+  T* Xn;                 // [P][NR] next stage vector (stage 4: the new state, or nullptr when Q alone receives it)
   T* Xn_hi;              // fp32 only: tf32 split of Xn for the next 3xTF32 GEMM
   T* Xn_lo;
   T* Qsave;              // stage 4: second copy of the new state (a chunk-trajectory slot of the adjoint recompute), or nullptr
@@ -197,7 +197,7 @@ __device__ __forceinline__ void stage_update_body(const UpdArgs<T>& a, const int
     else if constexpr (STAGE == 2) { Sr[b * NR] = fma(T(2), y[b], sv[b]); xn = fma(a.h2, y[b], q[b]); }
     else if constexpr (STAGE == 3) { Sr[b * NR] = fma(T(2), y[b], sv[b]); xn = fma(a.h, y[b], q[b]); }
     else { xn = fma(a.h6, sv[b] + y[b], q[b]); Qr[b * NR] = xn; if (a.Qsave) a.Qsave[o0 + b * NR] = xn; }
-    Xn[b * NR] = xn;
+    if (STAGE != 4 || a.Xn) Xn[b * NR] = xn;      // stage 4 may write the state array only (the host's stage_direct scheme)
     if constexpr (sizeof(T) == 4) {
       if (a.Xn_hi) {
         const float hi = __uint_as_float(pasif_large::f2tf32(xn));
