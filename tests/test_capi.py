@@ -33,6 +33,33 @@ def test_library_has_sm100a_kernels():
     assert "sm_100a" in out
 
 
+def test_dense_operator_fast_path_kernels_fit_their_register_budget():
+    """The update kernel of the dense-operator path is capped at 64 registers (4 resident CTAs per SM); its default
+    instantiations (4 trajectories per thread, one instance per thread) must not pay for that with local-memory traffic:
+    none in fp32, at most the stage-4 variant's few bytes in fp64.  The tcgen05 GEMM kernels never spill."""
+    out = subprocess.run(["cuobjdump", "-res-usage", capi.LIB_PATH], stdout=subprocess.PIPE, text=True).stdout
+    usage = {}
+    name = None
+    for line in out.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+            continue
+        m = re.search(r"REG:(\d+) STACK:(\d+)", line)
+        if m and name:
+            usage[name] = (int(m.group(1)), int(m.group(2)))
+            name = None
+    upd = {k: v for k, v in usage.items() if re.search(r"stage_update_kernelI[fd]Li4ELi\dELb[01]ELb1ELb[01]E", k)}
+    assert len(upd) == 20, sorted(upd)                    # 2 types x (4 stages x {forward, adjoint} + 2 half stages)
+    for k, (reg, stack) in upd.items():
+        assert reg <= 64, (k, reg)
+        assert stack == 0 or ("kernelId" in k and "Li4ELi4E" in k and stack <= 64), (k, stack)
+    gemm = {k: v for k, v in usage.items() if "tcgen05" in k}
+    assert len(gemm) >= 3
+    for k, (reg, stack) in gemm.items():
+        assert stack == 0, (k, stack)
+
+
 def test_pybind_module_exposes_reference_interface():
     sys.path.insert(0, os.path.join(ROOT, "pasif_b200"))
     import PASIfgpu
