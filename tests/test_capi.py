@@ -99,6 +99,18 @@ def _host(systems, jacobians=None, dtype="f64"):
     return p
 
 
+def test_missing_library_fails_loudly():
+    """No native library -> ImportError naming the build step, in a fresh interpreter (nothing else is tried)."""
+    code = ("import sys; sys.path.insert(0, %r)\n"
+            "from pasif_b200 import capi\n"
+            "import numpy as np\n"
+            "capi.Engine(np.ones((2, 10)), 16000, 10)\n") % ROOT
+    r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, PASIF_B200_LIB="/nonexistent/libpasif_b200.so"),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+    assert r.returncode != 0
+    assert "ImportError" in r.stderr and "is not built" in r.stderr
+
+
 def test_host_only_engine_refuses_to_solve():
     p = _host([wl.fit8_system()])
     with pytest.raises(capi.PasifError, match="host-only"):
