@@ -83,6 +83,9 @@ int pasif_get_gradient(pasif_engine* e, uint32_t save, double* out, uint64_t n_o
  * The _device variant writes N_adj values of the engine's compute type to a device pointer (for an NCCL all-reduce). */
 int pasif_get_gradient_reduced(pasif_engine* e, uint32_t save, double* out, uint64_t n_out);
 int pasif_get_gradient_reduced_device(pasif_engine* e, uint32_t save, void* device_out, uint64_t n_out);
+/* the same sum over excitations of the adjoint state the LAST pasif_get_gradient call left on the device (no recompute):
+ * lets a caller fetch the reference's un-reduced [e][j] result and feed the all-reduce from one evaluation */
+int pasif_reduce_last_gradient_device(pasif_engine* e, void* device_out, uint64_t n_out);
 
 /* introspection: "n_fwd", "n_adj", "n_excitations", "length", "numsteps", "fwd_classes", "fwd_instances",
  * "joint_classes", "joint_instances", "last_device_ms" (CUDA-event time of the last solve on the engine's stream),
@@ -95,7 +98,8 @@ int pasif_emit_patterns(pasif_engine* e, char* buf, uint64_t cap, uint64_t* need
  * no device needed (debugging aid: register use of the lane-block kernels) */
 int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t cap, uint64_t* needed);
 /* device pipe microbenchmarks (register-resident, no memory traffic): achieved TFLOP/s.  dtype PASIF_F64 / PASIF_F32: FMA pipe;
- * 2: mma.sync m8n8k4 f64 (DMMA); 3: mma.sync m16n8k8 tf32 (fp32 accumulate) */
+ * 2: mma.sync m8n8k4 f64 (DMMA); 3: mma.sync m16n8k8 tf32 (fp32 accumulate); 4: FMA pipe through packed fp32 pairs (FFMA2).
+ * The FMA loops carry 128 FMAs per iteration (>= 97 % of the issued instructions) */
 int pasif_fma_peak(int device, int dtype, double* tflops);
 /* isolated check of the dense-operator path's GEMM kernels (no reference counterpart: replaces the cusparseSpMM of
  * src/__GpuDriver.cu:795-807 for a dense shared K'): y[p][m] = sum_k kd[m][k] * x[p][k], kd [n][n], x / y [n_traj][n], row-major doubles.

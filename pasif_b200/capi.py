@@ -20,7 +20,7 @@ pasif_set_fwd_k pasif_set_fwd_gamma pasif_set_fwd_lambda pasif_set_fwd_psi pasif
 pasif_set_bwd_k pasif_set_bwd_gamma pasif_set_bwd_lambda pasif_set_bwd_psi pasif_set_bwd_force pasif_set_bwd_ic pasif_alloc_adjoint
 pasif_set_interp pasif_set_modulation pasif_set_option
 pasif_get_amplitudes pasif_trajectory_size pasif_get_trajectory pasif_get_gradient pasif_get_gradient_reduced
-pasif_get_gradient_reduced_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm pasif_debug_jit_log""".split()
+pasif_get_gradient_reduced_device pasif_reduce_last_gradient_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm pasif_debug_jit_log""".split()
 
 _lib = None
 _dp = C.POINTER(C.c_double)
@@ -57,6 +57,7 @@ def lib():
         L.pasif_get_gradient.argtypes = [C.c_void_p, C.c_uint32, _dp, C.c_uint64]
         L.pasif_get_gradient_reduced.argtypes = [C.c_void_p, C.c_uint32, _dp, C.c_uint64]
         L.pasif_get_gradient_reduced_device.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint64]
+        L.pasif_reduce_last_gradient_device.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
         L.pasif_query.argtypes = [C.c_void_p, C.c_char_p, _dp]
         L.pasif_emit_patterns.argtypes = [C.c_void_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
         L.pasif_debug_jit_log.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p, C.c_uint64, C.POINTER(C.c_uint64)]
@@ -202,6 +203,10 @@ class Engine:
     def _getGradientReducedDevice(self, device_ptr, save=0):
         self._check(lib().pasif_get_gradient_reduced_device(self._h, int(save), C.c_void_p(int(device_ptr)), int(self._query("n_adj"))))
 
+    def _reduceLastGradientDevice(self, device_ptr):
+        """sum over excitations of the adjoint state the last `_getGradient` left on the device -> device pointer"""
+        self._check(lib().pasif_reduce_last_gradient_device(self._h, C.c_void_p(int(device_ptr)), int(self._query("n_adj"))))
+
     def emit_patterns(self):
         need = C.c_uint64()
         self._check(lib().pasif_emit_patterns(self._h, None, 0, C.byref(need)))
@@ -220,7 +225,7 @@ class Engine:
 
 def fma_peak(device=0, dtype="f64"):
     v = C.c_double()
-    if lib().pasif_fma_peak(int(device), {"f64": 0, "f32": 1, "dmma": 2, "tf32_mma": 3}[dtype], C.byref(v)) != 0:
+    if lib().pasif_fma_peak(int(device), {"f64": 0, "f32": 1, "dmma": 2, "tf32_mma": 3, "f32x2": 4}[dtype], C.byref(v)) != 0:
         raise PasifError(lib().pasif_last_error(None).decode())
     return v.value
 

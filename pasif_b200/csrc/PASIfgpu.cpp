@@ -12,6 +12,7 @@
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
 
+#include <cstdint>
 #include <cstdlib>
 #include <stdexcept>
 #include <string>
@@ -103,6 +104,12 @@ class GpuDriver {
     { py::gil_scoped_release r; check(pasif_get_gradient_reduced(h, save, out.data(), out.size())); }
     return out;
   }
+  // excitation-summed adjoint state written to DEVICE memory of the engine's GPU (`device_ptr`: n_adj values of the
+  // engine's compute type, e.g. torch_tensor.data_ptr()); the write is complete when the call returns
+  void getGradientReducedDevice(uintptr_t device_ptr, uint save) {
+    py::gil_scoped_release r;
+    check(pasif_get_gradient_reduced_device(h, save, reinterpret_cast<void*>(device_ptr), (uint64_t)query("n_adj")));
+  }
 
  private:
   pasif_engine* h = nullptr;
@@ -170,6 +177,7 @@ PYBIND11_MODULE(PASIfgpu, m) {
       .def("_getGradient", &GpuDriver::getGradient, py::arg("save"))
       // additive
       .def("_getGradientReduced", &GpuDriver::getGradientReduced, py::arg("save") = 0)
+      .def("_getGradientReducedDevice", &GpuDriver::getGradientReducedDevice, py::arg("device_ptr"), py::arg("save") = 0)
       .def("_setOption", &GpuDriver::setOption, py::arg("key"), py::arg("value"))
       .def("_query", &GpuDriver::query, py::arg("key"));
 }

@@ -50,6 +50,7 @@ struct AotEntry {
   bool joint;
   const void* f64[3];  // forward | gradient-forward (dense save) | backward
   const void* f32[3];
+  const void* f32x2[3];  // fp32, two trajectories per thread (packed FFMA2; rk4_kernels.cuh)
 };
 std::vector<AotEntry>& aot_table() {
   static std::vector<AotEntry> t;
@@ -68,8 +69,12 @@ struct AotReg {
   __global__ void __launch_bounds__(PASIF_BLOCK) pasif_fwd_f32_##TR(const pasif::FwdArgs<float> a) {            \
     pasif::forward_body<float, TR, pasif::NoDense>(a);                                                          \
   }                                                                                                             \
+  __global__ void __launch_bounds__(PASIF_BLOCK) pasif_fwd_f32x2_##TR(const pasif::FwdArgs<float> a) {          \
+    pasif::forward_body<float, TR, pasif::NoDense, 2>(a);                                                       \
+  }                                                                                                             \
   AotReg reg_##TR(AotEntry{HASH, false, {(const void*)pasif_fwd_f64_##TR, nullptr, nullptr},                    \
-                           {(const void*)pasif_fwd_f32_##TR, nullptr, nullptr}});                               \
+                           {(const void*)pasif_fwd_f32_##TR, nullptr, nullptr},                                 \
+                           {(const void*)pasif_fwd_f32x2_##TR, nullptr, nullptr}});                             \
   }
 
 #define PASIF_AOT_JOINT(TR, HASH)                                                                               \
@@ -86,8 +91,15 @@ struct AotReg {
   __global__ void __launch_bounds__(PASIF_BLOCK) pasif_bwd_f32_##TR(const pasif::BwdArgs<float> a) {            \
     pasif::backward_body<float, TR::Adj>(a);                                                                    \
   }                                                                                                             \
+  __global__ void __launch_bounds__(PASIF_BLOCK) pasif_gfwd_f32x2_##TR(const pasif::FwdArgs<float> a) {         \
+    pasif::forward_body<float, TR::Fwd, TR::Adj, 2>(a);                                                         \
+  }                                                                                                             \
+  __global__ void __launch_bounds__(PASIF_BLOCK) pasif_bwd_f32x2_##TR(const pasif::BwdArgs<float> a) {          \
+    pasif::backward_body<float, TR::Adj, 2>(a);                                                                 \
+  }                                                                                                             \
   AotReg reg_##TR(AotEntry{HASH, true, {nullptr, (const void*)pasif_gfwd_f64_##TR, (const void*)pasif_bwd_f64_##TR}, \
-                           {nullptr, (const void*)pasif_gfwd_f32_##TR, (const void*)pasif_bwd_f32_##TR}});      \
+                           {nullptr, (const void*)pasif_gfwd_f32_##TR, (const void*)pasif_bwd_f32_##TR},        \
+                           {nullptr, (const void*)pasif_gfwd_f32x2_##TR, (const void*)pasif_bwd_f32x2_##TR}});  \
   }
 
 #if __has_include("patterns_aot.inc")
@@ -180,15 +192,42 @@ __global__ void reduce_excitations_kernel(const T* __restrict__ in, T* __restric
   if (threadIdx.x == 0 && jo < n) out[jo] = v;
 }
 
-// register-resident FMA-pipe peak: 8 independent chains per thread, no memory traffic in the loop
+// register-resident FMA-pipe peak: 16 independent chains per thread, 8 rounds per loop iteration = 128 FMAs against
+// 3 loop instructions (cuobjdump: the loop body is 128 FFMA / DFMA + IADD3 + ISETP + BRA, 97.7 % FMA; the r01 version
+// carried 8 FMAs per iteration and under-read the pipe by 9 %).  No memory traffic in the loop.
 template <typename T>
 __global__ void fma_peak_kernel(T* out, int iters, T a, T b) {
-  T x0 = T(threadIdx.x), x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+  T x[16];
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = T(threadIdx.x + k);
   for (int i = 0; i < iters; ++i) {
-    x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
-    x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = fma(x[k], a, b);
   }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = ((x0 + x1) + (x2 + x3)) + ((x4 + x5) + (x6 + x7));
+  T s = T(0);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) s += x[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+// the same with packed fp32 pairs (FFMA2): two FMAs per instruction slot -- the pipe's peak does not change, the issue
+// rate needed to reach it halves
+__global__ void fma2_peak_kernel(float2* out, int iters, float a, float b) {
+  float2 x[16];
+  const float2 a2 = make_float2(a, a), b2 = make_float2(b, b);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) x[k] = make_float2(float(threadIdx.x + k), float(k));
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int r = 0; r < 8; ++r)
+#pragma unroll
+      for (int k = 0; k < 16; ++k) x[k] = __ffma2_rn(x[k], a2, b2);
+  }
+  float2 s = make_float2(0.f, 0.f);
+#pragma unroll
+  for (int k = 0; k < 16; ++k) { s.x += x[k].x; s.y += x[k].y; }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
 
 // legacy tensor path peaks (mma.sync), 4 independent accumulator chains per warp
@@ -365,6 +404,7 @@ struct DevClass {
   std::unique_ptr<LargeClass, LargeClassDeleter> large;   // set for components beyond the register-resident range
   DevBuf coef, ic, varmap, coef_adj, ic_adj, varmap_adj;
   KernelHandle k_fwd, k_gfwd, k_bwd;
+  KernelHandle k_fwd2, k_gfwd2, k_bwd2;         // fp32 one-thread classes: two trajectories per thread (packed FFMA2)
   CUmodule module = nullptr;
   long long n_traj = 0;
 };
@@ -393,6 +433,7 @@ struct pasif_engine {
   DevBuf d_raw, d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;   // d_raw: excitations as handed over, [E][L] doubles
   PinnedBuf h_stage;                               // 2 slots of kStageSlot bytes
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  int d_user_kind = 0;                             // what d_user holds: 0 nothing | 1 amplitudes [E][N] | 2 adjoint state [E][N_adj]
   double last_h2d_ms = 0, last_d2h_ms = 0;         // host wall time of the last staged upload / download
   long long exc_rows = 0;
   bool exc_half = false;
@@ -411,6 +452,9 @@ struct pasif_engine {
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
   int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
   bool unit_on = true;                           // register kernels: K terms with coefficient exactly 1 become additions
+  bool pair_on = true;                           // fp32 one-thread classes: two trajectories per thread (packed FFMA2)
+  int pair_regs = 230;                           // register estimate up to which the pair kernels are used
+  long long pair_launches = 0;
   bool aot_on = true;                            // use the prebuilt kernels when a pattern matches (off: always specialise at run time)
   int jit_minb_fwd = 0, jit_minb_bwd = 0;        // one-thread kernels specialised at run time: minimum CTAs per SM (0: none)
   int lane_minb_fwd = 0, lane_minb_bwd = 0;      // lane-block kernels: minimum CTAs per SM handed to __launch_bounds__ (0: none)
@@ -473,6 +517,18 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
   const char* T = dtype == PASIF_F32 ? "float" : "double";
   // minb > 0: __launch_bounds__(PASIF_BLOCK, minb) -- caps the registers so that `minb` CTAs fit an SM (lane-block classes)
   auto lb = [](int minb) { return minb > 0 ? "__launch_bounds__(PASIF_BLOCK, " + std::to_string(minb) + ")" : std::string("__launch_bounds__(PASIF_BLOCK)"); };
+  const bool pair = dtype == PASIF_F32 && c.lanes == 1;
+  if (pair) {
+    if (!c.joint)
+      s += "extern \"C\" __global__ void " + lb(minb_fwd) + " pasif_k_fwd2(const pasif::FwdArgs<float> a) { pasif::forward_body<float, " +
+           c.name + ", pasif::NoDense, 2>(a); }\n";
+    else {
+      s += "extern \"C\" __global__ void " + lb(minb_fwd) + " pasif_k_gfwd2(const pasif::FwdArgs<float> a) { pasif::forward_body<float, " +
+           c.name + "::Fwd, " + c.name + "::Adj, 2>(a); }\n";
+      s += "extern \"C\" __global__ void " + lb(minb_bwd) + " pasif_k_bwd2(const pasif::BwdArgs<float> a) { pasif::backward_body<float, " +
+           c.name + "::Adj, 2>(a); }\n";
+    }
+  }
   if (!c.joint) {
     s += std::string("extern \"C\" __global__ void ") + lb(minb_fwd) + " pasif_k_fwd(const pasif::FwdArgs<" + T +
          "> a) { pasif::forward_body<" + T + ", " + c.name + ", pasif::NoDense>(a); }\n";
@@ -542,6 +598,7 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
     if (a.hash == c.hash && a.joint == c.joint) {
       const void* const* f = E.dtype == PASIF_F32 ? a.f32 : a.f64;
       dc.k_fwd.aot = f[0]; dc.k_gfwd.aot = f[1]; dc.k_bwd.aot = f[2];
+      if (E.dtype == PASIF_F32) { dc.k_fwd2.aot = a.f32x2[0]; dc.k_gfwd2.aot = a.f32x2[1]; dc.k_bwd2.aot = a.f32x2[2]; }
       ++E.aot_hits;
       return;
     }
@@ -563,6 +620,10 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
   };
   if (!c.joint) getf("pasif_k_fwd", &dc.k_fwd.jit);
   else { getf("pasif_k_gfwd", &dc.k_gfwd.jit); getf("pasif_k_bwd", &dc.k_bwd.jit); }
+  if (E.dtype == PASIF_F32 && c.lanes == 1) {
+    if (!c.joint) getf("pasif_k_fwd2", &dc.k_fwd2.jit);
+    else { getf("pasif_k_gfwd2", &dc.k_gfwd2.jit); getf("pasif_k_bwd2", &dc.k_bwd2.jit); }
+  }
 }
 
 cudaEvent_t prof_event(pasif_engine& E, int kind) {
@@ -599,6 +660,19 @@ void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& a
   if (E.profile) CUDA_CHECK(cudaEventRecord(prof_event(E, kind), st));
   ++E.last_launches;
   ++E.kind_launches[kind];
+}
+
+// fp32 one-thread classes with an even number of excitations run TWO trajectories per thread (packed FFMA2 kernels,
+// rk4_kernels.cuh): the pair (e, e+1) belongs to one instance and every 8-byte access is aligned.  Bit-identical to the
+// one-trajectory kernels; option pair=off keeps those.
+bool use_pairs(const pasif_engine& E, const DevClass& c) {
+  // register estimate of the pair kernels (calibrated with ptxas -v: 8-state system 100, 12-state adjoint 152): coefficients
+  // stay scalars, every state slot doubles; beyond the register file's comfortable range the one-trajectory kernels stay
+  const long long est = std::max<long long>(c.h.fwd.nc() + 8ll * c.h.fwd.N,
+                                            c.h.joint ? c.h.adj.nc() + 8ll * c.h.adj.N + 8ll * (long long)c.h.adj.nv.size() : 0) + 24;
+  if (est > E.pair_regs) return false;
+  return E.pair_on && E.dtype == PASIF_F32 && c.h.lanes == 1 && !c.large && E.E % 2 == 0 &&
+         (c.h.joint ? c.k_gfwd2.valid() && c.k_bwd2.valid() : c.k_fwd2.valid());
 }
 
 void free_classes(std::vector<DevClass>& v) {
@@ -857,9 +931,11 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
     } else {
       a.final_user = (T*)E.d_user.p;
     }
-    launch(E, c.k_fwd, c.n_traj, a, 0, nullptr, c.h.lanes);
+    if (use_pairs(E, c)) { launch(E, c.k_fwd2, c.n_traj / 2, a, 0, nullptr, 1); ++E.pair_launches; }
+    else launch(E, c.k_fwd, c.n_traj, a, 0, nullptr, c.h.lanes);
   }
   end_timing(E);
+  if (!trajectory) E.d_user_kind = 1;
   download<T>(E, trajectory ? E.d_traj.p : E.d_user.p, out, trajectory ? n_slots * width : width);
 }
 
@@ -890,6 +966,12 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     if (c.large) { large_solve_gradient<T>(E, c, save, d_user_out); continue; }
     const long long P = c.n_traj;
     const int NF = c.h.fwd.N, NA = c.h.adj.N, NV = (int)c.h.adj.nv.size();
+    // two trajectories per thread (fp32): half as many threads, pair kernels on both sides (they share the chunk-trajectory layout)
+    const bool pairs = use_pairs(E, c);
+    const KernelHandle& k_gfwd = pairs ? c.k_gfwd2 : c.k_gfwd;
+    const KernelHandle& k_bwd = pairs ? c.k_bwd2 : c.k_bwd;
+    const long long PT = pairs ? P / 2 : P;        // threads
+    if (pairs) ++E.pair_launches;
     E.d_lam.reserve((size_t)NA * P * sizeof(T));
     {
       const long long tot = (long long)NA * P;
@@ -942,7 +1024,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         a.save_ptr = ckpt; a.save_every = (int)chunk; a.save_layout = 0; a.save_slots = (int)nsp;
         if (!E.compat_clean) {
           a.save_phase = 0;                        // slot j <- state AFTER step j*c (quirk A1)
-          launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
+          launch(E, k_gfwd, PT, a, 1, nullptr, c.h.lanes);
         } else {
           a.save_phase = 1;                        // slot j <- state BEFORE step j*c; slot 0 = initial condition
           const long long tot = (long long)NF * P;
@@ -952,13 +1034,13 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
           const long long t_split = std::min<long long>(n, sp_store * chunk);
           if (t_split > 0) {                       // checkpoints only
             a.t1 = (int)t_split;
-            launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
+            launch(E, k_gfwd, PT, a, 1, nullptr, c.h.lanes);
           }
           if (t_split < n) {                       // checkpoints + chunk trajectories, continuing from slot sp_store
             a.q_in = ckpt + (size_t)sp_store * slot_elems;
             a.t0 = (int)t_split; a.t1 = (int)n;
             a.dense_ptr = (T*)E.d_tail.p;
-            launch(E, c.k_gfwd, P, a, 1, nullptr, c.h.lanes);
+            launch(E, k_gfwd, PT, a, 1, nullptr, c.h.lanes);
           }
         }
       }
@@ -986,7 +1068,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
           a.q_in = ckpt + (size_t)sp * slot_elems;
           a.t0 = (int)start; a.t1 = (int)end;
           a.dense_ptr = dense_buf[buf];
-          launch(E, c.k_gfwd, P, a, 1, E.stream, c.h.lanes);
+          launch(E, k_gfwd, PT, a, 1, E.stream, c.h.lanes);
         }
         if (ovl) {                                 // (for a stored chunk: orders the adjoint stream after the sweep)
           CUDA_CHECK(cudaEventRecord(E.ev_rec[buf], E.stream));
@@ -1004,7 +1086,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         b.alias_local = E.compat_clean ? -1000000 : (int)(S_global - sp);
         b.n_inst = c.h.n_inst; b.E = (int)E.E; b.n_traj = (int)P;
         b.h = a.h; b.h2 = a.h2; b.h6 = a.h6;
-        launch(E, c.k_bwd, P, b, 2, sB, c.h.lanes);
+        launch(E, k_bwd, PT, b, 2, sB, c.h.lanes);
         if (ovl) CUDA_CHECK(cudaEventRecord(E.ev_bwd[buf], sB));
         last_buf = buf;
         ++it;
@@ -1040,8 +1122,22 @@ void gradient_entry(pasif_engine& E, uint32_t save, double* out, uint64_t n_out,
     ++E.last_launches;
   }
   end_timing(E);
+  E.d_user_kind = 2;
   if (reduced) { if (!dev_out) download<T>(E, red, out, E.bwd.n); }
   else download<T>(E, E.d_user.p, out, width);
+}
+
+// sum over excitations of the adjoint state the last pasif_get_gradient left on the device, written to device memory
+template <typename T>
+void reduce_last(pasif_engine& E, void* dev_out, uint64_t n_out) {
+  E.use_device();
+  if (E.d_user_kind != 2) throw std::runtime_error("no gradient on the device: call pasif_get_gradient first");
+  if (!dev_out) throw std::runtime_error("device_out is NULL");
+  if (n_out != E.bwd.n) throw std::runtime_error("reduced gradient buffer must hold N_adj values");
+  reduce_excitations_kernel<T><<<(unsigned)((E.bwd.n + 31) / 32), dim3(32, 32), 0, E.stream>>>(
+      (const T*)E.d_user.p, (T*)dev_out, (int)E.E, (int)E.bwd.n);
+  CUDA_CHECK(cudaGetLastError());
+  CUDA_CHECK(cudaStreamSynchronize(E.stream));
 }
 
 void set_tensor(Tensor& t, int order, const uint32_t* dims, const double* values, const uint32_t* indices, uint32_t nnz) {
@@ -1292,6 +1388,10 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->lanes_max = (v == "off" || v == "0") ? 0 : (v == "on" ? 1024 : std::atoi(v.c_str()));
   } else if (k == "unit_terms") {
     e->unit_on = (v == "on" || v == "1");
+  } else if (k == "pair") {
+    e->pair_on = (v == "on" || v == "1");
+  } else if (k == "pair_regs") {
+    e->pair_regs = std::atoi(v.c_str());
   } else if (k == "aot") {
     e->aot_on = (v == "on" || v == "1");
   } else if (k == "jit_minb_fwd") {
@@ -1363,6 +1463,13 @@ int pasif_get_gradient_reduced_device(pasif_engine* e, uint32_t save, void* devi
   PASIF_CATCH(e)
 }
 
+int pasif_reduce_last_gradient_device(pasif_engine* e, void* device_out, uint64_t n_out) {
+  PASIF_TRY(e)
+  if (e->dtype == PASIF_F32) reduce_last<float>(*e, device_out, n_out);
+  else reduce_last<double>(*e, device_out, n_out);
+  PASIF_CATCH(e)
+}
+
 int pasif_query(const pasif_engine* e, const char* key, double* value) {
   if (!e || !key || !value) return 1;
   const std::string k(key);
@@ -1385,6 +1492,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "jit_compiles") *value = (double)e->jit_compiles;
   else if (k == "jit_cache_hits") *value = (double)e->jit_cache_hits;
   else if (k == "aot_hits") *value = (double)e->aot_hits;
+  else if (k == "pair_launches") *value = (double)e->pair_launches;
   else if (k == "dtype") *value = e->dtype;
   else if (k == "large_classes") *value = (double)e->large_classes;
   else if (k == "lane_classes") *value = (double)e->lane_classes;
@@ -1501,7 +1609,7 @@ int pasif_fma_peak(int device, int dtype, double* tflops) {
     CUDA_CHECK(cudaSetDevice(device));
     cudaDeviceProp prop;
     CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
-    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 16;
+    const int threads = 256, blocks = prop.multiProcessorCount * 8, iters = 1 << 12;   // x 128 FMAs per iteration
     void* out = nullptr;
     CUDA_CHECK(cudaMalloc(&out, (size_t)threads * blocks * 8));
     cudaEvent_t a, b;
@@ -1512,8 +1620,10 @@ int pasif_fma_peak(int device, int dtype, double* tflops) {
       CUDA_CHECK(cudaEventRecord(a));
       if (dtype == PASIF_F32) fma_peak_kernel<float><<<blocks, threads>>>((float*)out, iters, 0.999f, 1e-3f);
       else if (dtype == PASIF_F64) fma_peak_kernel<double><<<blocks, threads>>>((double*)out, iters, 0.999, 1e-3);
-      else if (dtype == 2) dmma_peak_kernel<<<blocks, threads>>>((double*)out, iters / 8);
-      else tf32_mma_peak_kernel<<<blocks, threads>>>((float*)out, iters / 8);
+      else if (dtype == 2) dmma_peak_kernel<<<blocks, threads>>>((double*)out, iters * 2);
+      else if (dtype == 3) tf32_mma_peak_kernel<<<blocks, threads>>>((float*)out, iters * 2);
+      else if (dtype == 4) fma2_peak_kernel<<<blocks, threads>>>((float2*)out, iters / 2, 0.999f, 1e-3f);
+      else throw std::runtime_error("pasif_fma_peak: dtype must be 0 (f64) | 1 (f32) | 2 (dmma) | 3 (tf32 mma.sync) | 4 (f32x2)");
       CUDA_CHECK(cudaEventRecord(b));
       CUDA_CHECK(cudaEventSynchronize(b));
       float ms = 0;
@@ -1522,9 +1632,9 @@ int pasif_fma_peak(int device, int dtype, double* tflops) {
     }
     CUDA_CHECK(cudaGetLastError());
     cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(out);
-    if (dtype == 2) *tflops = 2.0 * 256.0 * 4.0 * (double)(iters / 8) * (threads / 32) * blocks / (best * 1e-3) / 1e12;        // m8n8k4
-    else if (dtype == 3) *tflops = 2.0 * 1024.0 * 4.0 * (double)(iters / 8) * (threads / 32) * blocks / (best * 1e-3) / 1e12;  // m16n8k8
-    else *tflops = 2.0 * 8.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;
+    if (dtype == 2) *tflops = 2.0 * 256.0 * 4.0 * (double)(iters * 2) * (threads / 32) * blocks / (best * 1e-3) / 1e12;        // m8n8k4
+    else if (dtype == 3) *tflops = 2.0 * 1024.0 * 4.0 * (double)(iters * 2) * (threads / 32) * blocks / (best * 1e-3) / 1e12;  // m16n8k8
+    else *tflops = 2.0 * 128.0 * (double)iters * threads * blocks / (best * 1e-3) / 1e12;     // f32x2: iters / 2 x 256 FMAs
   } catch (const std::exception& ex) {
     g_create_error = ex.what();
     return 2;

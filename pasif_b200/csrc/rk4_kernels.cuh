@@ -112,16 +112,45 @@ PASIF_DEV void load_vec(const T* src, T (&v)[NV > 0 ? NV : 1]) {
   }
 }
 
+// ------------------------------------------------------------------------------------------------ packed fp32 pairs
+// W = 2 (fp32 only): one thread integrates TWO trajectories -- excitations e, e+1 of the same instance -- as the two
+// halves of 64-bit register pairs, on sm_100's packed FFMA2 / FMUL2 / FADD2 (PTX fma/mul/add.rn.f32x2).  Each half is
+// rounded exactly like the scalar instruction, so results are bit-identical to W = 1; what changes is the issue
+// rate: one instruction slot per two FMAs, and the coefficient (shared by the pair) enters as a scalar broadcast
+// operand (`FFMA2 R0, R3.F32, R4.F32x2.HI_LO, R8.F32x2.HI_LO`), so it still costs one register.  The one-thread
+// kernels are issue-bound (r01 ncu: 82 % of the issue slots for 75 % FMA-pipe activity); pairing halves the FP
+// issue slots and shares loop / address arithmetic between two trajectories.
+using ::fma;                                         // the scalar kernels keep the built-in fma next to the overloads below
+struct f32x2 { float2 v; };
+PASIF_DEV f32x2 fma(f32x2 a, f32x2 b, f32x2 c) { return f32x2{__ffma2_rn(a.v, b.v, c.v)}; }
+PASIF_DEV f32x2 fma(float a, f32x2 b, f32x2 c) { return f32x2{__ffma2_rn(make_float2(a, a), b.v, c.v)}; }
+PASIF_DEV f32x2 operator*(f32x2 a, f32x2 b) { return f32x2{__fmul2_rn(a.v, b.v)}; }
+PASIF_DEV f32x2 operator*(float a, f32x2 b) { return f32x2{__fmul2_rn(make_float2(a, a), b.v)}; }
+PASIF_DEV f32x2 operator+(f32x2 a, f32x2 b) { return f32x2{__fadd2_rn(a.v, b.v)}; }
+
+template <typename T, int W> struct Vec { typedef T type; };
+template <> struct Vec<float, 2> { typedef f32x2 type; };
+template <typename V> PASIF_DEV V vzero() { return V(0); }
+template <typename V, typename T> PASIF_DEV V bcast(T a) { return a; }
+template <> PASIF_DEV f32x2 bcast<f32x2, float>(float a) { return f32x2{make_float2(a, a)}; }
+template <> PASIF_DEV f32x2 vzero<f32x2>() { return f32x2{make_float2(0.f, 0.f)}; }
+// W consecutive trajectories of a trajectory-minor array (8-byte access for a pair: n_traj and the pair index are even)
+template <typename V, typename T> PASIF_DEV V ldv(const T* p) { return *reinterpret_cast<const V*>(p); }
+template <typename V, typename T> PASIF_DEV void stv(T* p, V v) { *reinterpret_cast<V*>(p) = v; }
+template <typename T> PASIF_DEV T half_of(T v, int) { return v; }
+PASIF_DEV float half_of(f32x2 v, int w) { return w ? v.v.y : v.v.x; }
+
 // ------------------------------------------------------------------------------------------------ lane-block classes
 // P::G > 1: a component too large for one thread is integrated by a group of G consecutive threads (lane_split.hpp).
 // Every lane owns P::N rows; before each derivative evaluation it publishes the P::NPUB slots other lanes read and
 // fetches its P::H halo operands (slot pub_slot(hx_pub(h)) of lane (lane + hx_delta(h)) mod G) through a
 // double-buffered shared-memory array: one group barrier per exchange.  Thread index p -> lane = p % G,
 // trajectory = p / G = instance * E + e, virtual instance = instance * G + lane.
-template <typename T>
+// (V: value type of a state slot -- T, or a packed pair in the two-trajectory kernels, which have no lane groups)
+template <typename V>
 struct LaneCtx {
-  T* sx;            // [2][NPUB][PASIF_BLOCK]  state / adjoint-state exchange
-  T* sp;            // [2][NPPUB][PASIF_BLOCK] set-point (forward state) exchange of the adjoint kernel
+  V* sx;            // [2][NPUB][PASIF_BLOCK]  state / adjoint-state exchange
+  V* sp;            // [2][NPPUB][PASIF_BLOCK] set-point (forward state) exchange of the adjoint kernel
   int bx, bp;       // current buffer of each
   int tid, gbase, lane;
 };
@@ -131,10 +160,10 @@ PASIF_DEV void group_sync(int tid) {
   else if constexpr (G >= PASIF_BLOCK) __syncthreads();
   else asm volatile("bar.sync %0, %1;" ::"r"(1 + tid / G), "n"(G) : "memory");   // one named barrier per group of the CTA
 }
-template <typename T, class P, int NXE>
-PASIF_DEV void exchange_x(T (&xe)[NXE], LaneCtx<T>& cx) {
+template <typename V, class P, int NXE>
+PASIF_DEV void exchange_x(V (&xe)[NXE], LaneCtx<V>& cx) {
   if constexpr (P::G > 1 && P::H > 0) {
-    T* b = cx.sx + cx.bx * (P::NPUB * PASIF_BLOCK);
+    V* b = cx.sx + cx.bx * (P::NPUB * PASIF_BLOCK);
 #pragma unroll
     for (int k = 0; k < P::NPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = xe[P::pub_slot(k)];
     group_sync<P::G>(cx.tid);
@@ -144,10 +173,10 @@ PASIF_DEV void exchange_x(T (&xe)[NXE], LaneCtx<T>& cx) {
     cx.bx ^= 1;
   }
 }
-template <typename T, class P, int NPE>
-PASIF_DEV void exchange_p(T (&pe)[NPE], LaneCtx<T>& cx) {
+template <typename V, class P, int NPE>
+PASIF_DEV void exchange_p(V (&pe)[NPE], LaneCtx<V>& cx) {
   if constexpr (P::G > 1 && P::HP > 0) {
-    T* b = cx.sp + cx.bp * (P::NPPUB * PASIF_BLOCK);
+    V* b = cx.sp + cx.bp * (P::NPPUB * PASIF_BLOCK);
 #pragma unroll
     for (int k = 0; k < P::NPPUB; ++k) b[k * PASIF_BLOCK + cx.tid] = pe[P::ppub_slot(k)];
     group_sync<P::G>(cx.tid);
@@ -161,11 +190,12 @@ PASIF_DEV void exchange_p(T (&pe)[NPE], LaneCtx<T>& cx) {
 // ------------------------------------------------------------------------------------------------ derivative
 // y = K x + Gamma:(x,p) + Lambda:(x,p,p) + Psi:(x,p,p,p) + F fe        (forward: p == x)
 // x / p may be longer than the row count: lane-block classes append the halo entries (operands owned by other lanes)
-template <typename T, class P, int NX, int NP_>
-PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::NC > 0 ? P::NC : 1], T fe,
-                          T (&y)[P::N]) {
+// V = T: one trajectory; V = f32x2: two trajectories of one instance (the coefficients c stay scalars)
+template <typename V, typename T, class P, int NX, int NP_>
+PASIF_DEV void derivative(const V (&x)[NX], const V (&p)[NP_], const T (&c)[P::NC > 0 ? P::NC : 1], V fe,
+                          V (&y)[P::N]) {
 #pragma unroll
-  for (int r = 0; r < P::N; ++r) y[r] = T(0);
+  for (int r = 0; r < P::N; ++r) y[r] = vzero<V>();
 #pragma unroll
   for (int k = 0; k < P::NNZK; ++k) {
     // unit coefficient (x' = v): fma(1, x, y) == y + x and fma(1, x, 0) == x, bit for bit (up to the sign of a zero) -- no
@@ -187,36 +217,40 @@ PASIF_DEV void derivative(const T (&x)[NX], const T (&p)[NP_], const T (&c)[P::N
 }
 
 // one classical RK4 step of the forward system; fa/fb/fc = force sample of stage 1 / stages 2,3 / stage 4
-template <typename T, class P>
-PASIF_DEV void rk4_forward_step(T (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1], T fa, T fb, T fc, T h, T h2, T h6,
-                                LaneCtx<T>& cx) {
+template <typename V, typename T, class P>
+PASIF_DEV void rk4_forward_step(V (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1], V fa, V fb, V fc, T h, T h2, T h6,
+                                LaneCtx<V>& cx) {
   constexpr int NXE = P::N + P::H;
-  T m[P::N], s[P::N], mi[NXE];
+  V m[P::N], s[P::N], mi[NXE];
 #pragma unroll
   for (int i = 0; i < P::N; ++i) mi[i] = q[i];
-  exchange_x<T, P, NXE>(mi, cx);
-  derivative<T, P, NXE, NXE>(mi, mi, c, fa, m);
+  exchange_x<V, P, NXE>(mi, cx);
+  derivative<V, T, P, NXE, NXE>(mi, mi, c, fa, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = m[i]; mi[i] = fma(h2, m[i], q[i]); }
-  exchange_x<T, P, NXE>(mi, cx);
-  derivative<T, P, NXE, NXE>(mi, mi, c, fb, m);
+  exchange_x<V, P, NXE>(mi, cx);
+  derivative<V, T, P, NXE, NXE>(mi, mi, c, fb, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h2, m[i], q[i]); }
-  exchange_x<T, P, NXE>(mi, cx);
-  derivative<T, P, NXE, NXE>(mi, mi, c, fb, m);
+  exchange_x<V, P, NXE>(mi, cx);
+  derivative<V, T, P, NXE, NXE>(mi, mi, c, fb, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) { s[i] = fma(T(2), m[i], s[i]); mi[i] = fma(h, m[i], q[i]); }
-  exchange_x<T, P, NXE>(mi, cx);
-  derivative<T, P, NXE, NXE>(mi, mi, c, fc, m);
+  exchange_x<V, P, NXE>(mi, cx);
+  derivative<V, T, P, NXE, NXE>(mi, mi, c, fc, m);
 #pragma unroll
   for (int i = 0; i < P::N; ++i) q[i] = fma(h6, s[i] + m[i], q[i]);
 }
 
 // ------------------------------------------------------------------------------------------------ forward kernel
 // PF: forward pattern.  DV: list of forward variables written by the dense save (DV::NV may be 0).
-template <typename T, class PF, class DV>
+// W: trajectories per thread (2: packed fp32 pairs, G == 1 and E even; the dense save of a pair is ONE vector of
+// 2 NV values in [variable][half] order -- written and read only by the pair kernels of the same class).
+template <typename T, class PF, class DV, int W = 1>
 PASIF_DEV void forward_body(const FwdArgs<T>& a) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  typedef typename Vec<T, W>::type V;
+  static_assert(W == 1 || PF::G == 1, "two trajectories per thread: one-thread classes only");
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) * W;     // first trajectory of the thread
   if (p >= a.n_traj) return;                       // lane-block classes: whole groups leave together (n_traj % G == 0)
   constexpr int G = PF::G;
   const int lane = p & (G - 1);
@@ -226,19 +260,19 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
   constexpr int N = PF::N;
   constexpr int NC = PF::NC > 0 ? PF::NC : 1;
   constexpr int SXN = (G > 1 && PF::H > 0) ? 2 * PF::NPUB * PASIF_BLOCK : 1;
-  __shared__ T sm_x[SXN];
-  LaneCtx<T> cx{sm_x, nullptr, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
+  __shared__ V sm_x[SXN];
+  LaneCtx<V> cx{sm_x, nullptr, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
 
   T c[NC];
 #pragma unroll
   for (int k = 0; k < PF::NC; ++k) c[k] = a.coef[(long long)k * a.n_inst + inst];
-  T q[N];
+  V q[N];
   if (a.q_in) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = a.q_in[(long long)i * a.n_traj + p];
+    for (int i = 0; i < N; ++i) q[i] = ldv<V>(a.q_in + (long long)i * a.n_traj + p);
   } else {
 #pragma unroll
-    for (int i = 0; i < N; ++i) q[i] = a.ic[(long long)i * a.n_inst + inst];
+    for (int i = 0; i < N; ++i) q[i] = bcast<V>(a.ic[(long long)i * a.n_inst + inst]);
   }
 
   const T h = a.h, h2 = a.h2, h6 = a.h6;
@@ -251,16 +285,17 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
     save_cnt = save_slot * a.save_every - u;                    // steps (beyond t0) until that save fires
   }
   constexpr int NVD = DV::NV > 0 ? DV::NV : 1;
+  constexpr int NVDW = DV::NV > 0 ? DV::NV * W : 1;
   T* dense = a.dense_ptr ? a.dense_ptr + (long long)p * DV::NV : nullptr;
   const long long dense_stride = (long long)a.n_traj * DV::NV;
 
   // everything that follows one RK4 step: dense save of the needed variables, periodic checkpoint / trajectory save
   auto after_step = [&]() {
     if (DV::NV > 0 && dense) {
-      T dv[NVD];
+      V dv[NVD];
 #pragma unroll
       for (int v = 0; v < DV::NV; ++v) dv[v] = q[DV::nv(v)];
-      store_vec<T, DV::NV>(dense, dv);
+      store_vec<T, DV::NV * W>(dense, reinterpret_cast<const T(&)[NVDW]>(dv));
       dense += dense_stride;
     }
     if (save_cnt == 0) {
@@ -268,13 +303,16 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
         if (a.save_layout == 0) {
           T* dst = a.save_ptr + ((long long)save_slot * N) * a.n_traj + p;
 #pragma unroll
-          for (int i = 0; i < N; ++i) dst[(long long)i * a.n_traj] = q[i];
+          for (int i = 0; i < N; ++i) stv<V>(dst + (long long)i * a.n_traj, q[i]);
         } else {
-          T* dst = a.save_ptr + ((long long)save_slot * E + e) * a.n_glob;
 #pragma unroll
-          for (int i = 0; i < N; ++i) {
-            const int g = a.varmap[(long long)i * a.n_inst + inst];
-            if (G == 1 || g >= 0) dst[g] = q[i];                                 // -1: padding slot of a lane
+          for (int w = 0; w < W; ++w) {
+            T* dst = a.save_ptr + ((long long)save_slot * E + e + w) * a.n_glob;
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+              const int g = a.varmap[(long long)i * a.n_inst + inst];
+              if (G == 1 || g >= 0) dst[g] = half_of(q[i], w);                     // -1: padding slot of a lane
+            }
           }
         }
       }
@@ -288,52 +326,55 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
     // gated excitation samples e[t .. t+4] in registers; the time loop is unrolled by 4 so that the next four samples
     // are requested a whole block (4 steps) before their first use and no register shuffling is left per step
     const T* ex = a.exc + (long long)a.t0 * E + e;
-    T e0 = ex[0], e1 = ex[E], e2 = ex[2 * E], e3 = ex[3 * E], e4 = ex[4 * E];   // buffer is zero-padded past t1
+    V e0 = ldv<V>(ex), e1 = ldv<V>(ex + E), e2 = ldv<V>(ex + 2 * E), e3 = ldv<V>(ex + 3 * E), e4 = ldv<V>(ex + 4 * E);   // buffer is zero-padded past t1
     ex += 5 * E;
     int t = a.t0;
     // patterns with many terms (lane-block classes): one step per iteration, or the body outgrows the instruction cache
     // (ncu on the 256-DOF chain: 0.73 "no instruction" stalls per issue with the 4x body)
     if constexpr (PF::NC <= 40) {
       for (; t + 4 <= a.t1; t += 4) {
-        const T n0 = ex[0], n1 = ex[E], n2 = ex[2 * E], n3 = ex[3 * E];           // e[t+5 .. t+8]
+        const V n0 = ldv<V>(ex), n1 = ldv<V>(ex + E), n2 = ldv<V>(ex + 2 * E), n3 = ldv<V>(ex + 3 * E);           // e[t+5 .. t+8]
         ex += 4 * E;
-        rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
-        rk4_forward_step<T, PF>(q, c, e1, e1, e2, h, h2, h6, cx); after_step();
-        rk4_forward_step<T, PF>(q, c, e2, e2, e3, h, h2, h6, cx); after_step();
-        rk4_forward_step<T, PF>(q, c, e3, e3, e4, h, h2, h6, cx); after_step();
+        rk4_forward_step<V, T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
+        rk4_forward_step<V, T, PF>(q, c, e1, e1, e2, h, h2, h6, cx); after_step();
+        rk4_forward_step<V, T, PF>(q, c, e2, e2, e3, h, h2, h6, cx); after_step();
+        rk4_forward_step<V, T, PF>(q, c, e3, e3, e4, h, h2, h6, cx); after_step();
         e0 = e4; e1 = n0; e2 = n1; e3 = n2; e4 = n3;
       }
     }
     for (; t < a.t1; ++t) {
-      const T n0 = *ex;
+      const V n0 = ldv<V>(ex);
       ex += E;
-      rk4_forward_step<T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
+      rk4_forward_step<V, T, PF>(q, c, e0, e0, e1, h, h2, h6, cx); after_step();
       e0 = e1; e1 = e2; e2 = e3; e3 = e4; e4 = n0;
     }
   } else {
     // half-step mode (interpolation table): f[2t], f[2t+1], f[2t+2] -- preprocessed on the device by
     // prep_exc_half_kernel; two new samples per step, requested one step ahead
     const T* ex = a.exc + (long long)(2 * a.t0) * E + e;
-    T f0 = ex[0], f1 = ex[E], f2 = ex[2 * E];
+    V f0 = ldv<V>(ex), f1 = ldv<V>(ex + E), f2 = ldv<V>(ex + 2 * E);
     ex += 3 * E;
     for (int t = a.t0; t < a.t1; ++t) {
-      const T g1 = ex[0], g2 = ex[E];                                            // f[2t+3], f[2t+4]
+      const V g1 = ldv<V>(ex), g2 = ldv<V>(ex + E);                                            // f[2t+3], f[2t+4]
       ex += 2 * E;
-      rk4_forward_step<T, PF>(q, c, f0, f1, f2, h, h2, h6, cx); after_step();
+      rk4_forward_step<V, T, PF>(q, c, f0, f1, f2, h, h2, h6, cx); after_step();
       f0 = f2; f1 = g1; f2 = g2;
     }
   }
 
   if (a.q_out) {
 #pragma unroll
-    for (int i = 0; i < N; ++i) a.q_out[(long long)i * a.n_traj + p] = q[i];
+    for (int i = 0; i < N; ++i) stv<V>(a.q_out + (long long)i * a.n_traj + p, q[i]);
   }
   if (a.final_user) {
-    T* dst = a.final_user + (long long)e * a.n_glob;
 #pragma unroll
-    for (int i = 0; i < N; ++i) {
-      const int g = a.varmap[(long long)i * a.n_inst + inst];
-      if (G == 1 || g >= 0) dst[g] = q[i];
+    for (int w = 0; w < W; ++w) {
+      T* dst = a.final_user + (long long)(e + w) * a.n_glob;
+#pragma unroll
+      for (int i = 0; i < N; ++i) {
+        const int g = a.varmap[(long long)i * a.n_inst + inst];
+        if (G == 1 || g >= 0) dst[g] = half_of(q[i], w);
+      }
     }
   }
 }
@@ -342,9 +383,11 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
 // PA: adjoint pattern: N = adjoint state size, tensor "p" indices refer to the needed-forward-variable list
 // (PA::NV entries, PA::nv(v) = local forward index).  RK4 on the unforced adjoint ODE, walking the recomputed
 // chunk backwards; forward state per stage = q_i, (q_i + q_{i-1})/2, q_{i-1}  (src/__GpuDriver.cu:746-783).
-template <typename T, class PA>
+template <typename T, class PA, int W = 1>
 PASIF_DEV void backward_body(const BwdArgs<T>& a) {
-  const int p = blockIdx.x * blockDim.x + threadIdx.x;
+  typedef typename Vec<T, W>::type V;
+  static_assert(W == 1 || PA::G == 1, "two trajectories per thread: one-thread classes only");
+  const int p = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   if (p >= a.n_traj) return;
   constexpr int G = PA::G;
   const int lane = p & (G - 1);
@@ -352,69 +395,70 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   constexpr int N = PA::N;
   constexpr int NC = PA::NC > 0 ? PA::NC : 1;
   constexpr int NV = PA::NV > 0 ? PA::NV : 1;
+  constexpr int NVW = PA::NV > 0 ? PA::NV * W : 1;
   constexpr int NXE = N + PA::H;                   // adjoint state + halo
   constexpr int NPE = NV + PA::HP;                 // needed forward variables + halo
   constexpr int SXN = (G > 1 && PA::H > 0) ? 2 * PA::NPUB * PASIF_BLOCK : 1;
   constexpr int SPN = (G > 1 && PA::HP > 0) ? 2 * PA::NPPUB * PASIF_BLOCK : 1;
-  __shared__ T sm_x[SXN];
-  __shared__ T sm_p[SPN];
-  LaneCtx<T> cx{sm_x, sm_p, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
+  __shared__ V sm_x[SXN];
+  __shared__ V sm_p[SPN];
+  LaneCtx<V> cx{sm_x, sm_p, 0, 0, (int)threadIdx.x, (int)threadIdx.x - lane, lane};
 
   T c[NC];
 #pragma unroll
   for (int k = 0; k < PA::NC; ++k) c[k] = a.coef[(long long)k * a.n_inst + inst];
-  T lam[N];
+  V lam[N];
 #pragma unroll
-  for (int i = 0; i < N; ++i) lam[i] = a.lam[(long long)i * a.n_traj + p];
+  for (int i = 0; i < N; ++i) lam[i] = ldv<V>(a.lam + (long long)i * a.n_traj + p);
 
   const T h = a.h, h2 = a.h2, h6 = a.h6;
   const long long stride = (long long)PA::NV * a.n_traj;
   const T* d = a.dense + (long long)p * PA::NV + (long long)(a.len - 1) * stride;    // state index i = len-1
-  T qa[NPE], qn[NV], qh[NPE];
-  load_vec<T, PA::NV>(d, reinterpret_cast<T(&)[NV]>(qa));
-  exchange_p<T, PA, NPE>(qa, cx);
+  V qa[NPE], qn[NV], qh[NPE];
+  load_vec<T, PA::NV * W>(d, reinterpret_cast<T(&)[NVW]>(qa));
+  exchange_p<V, PA, NPE>(qa, cx);
   // software prefetch: qn = state i-1 of the CURRENT iteration, loaded one iteration ahead
-  if (a.len >= 2) load_vec<T, PA::NV>(d - stride, qn);
+  if (a.len >= 2) load_vec<T, PA::NV * W>(d - stride, reinterpret_cast<T(&)[NVW]>(qn));
   else {
 #pragma unroll
-    for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
+    for (int v = 0; v < PA::NV; ++v) qn[v] = ldv<V>(a.prev + (long long)PA::nv(v) * a.n_traj + p);
   }
 
   for (int i = a.len - 1; i >= 0; --i) {
     // qb = forward state of index i-1.  Literal-reference mode: when i-1 is the aliased scratch slot the reference
     // reads back what it has just written there, i.e. the current qa.
-    T qb[NPE];
+    V qb[NPE];
     const bool aliased = (i - 1 == a.alias_local);
 #pragma unroll
     for (int v = 0; v < PA::NV; ++v) qb[v] = aliased ? qa[v] : qn[v];
-    exchange_p<T, PA, NPE>(qb, cx);
+    exchange_p<V, PA, NPE>(qb, cx);
     // prefetch state i-2 for the next iteration
-    if (i >= 2) load_vec<T, PA::NV>(d - 2 * stride, qn);
+    if (i >= 2) load_vec<T, PA::NV * W>(d - 2 * stride, reinterpret_cast<T(&)[NVW]>(qn));
     else if (i == 1) {
 #pragma unroll
-      for (int v = 0; v < PA::NV; ++v) qn[v] = a.prev[(long long)PA::nv(v) * a.n_traj + p];
+      for (int v = 0; v < PA::NV; ++v) qn[v] = ldv<V>(a.prev + (long long)PA::nv(v) * a.n_traj + p);
     }
     d -= stride;
 #pragma unroll
     for (int v = 0; v < PA::NV + PA::HP; ++v) qh[v] = T(.5) * (qa[v] + qb[v]);
 
-    T m[N], s[N], mi[NXE];
+    V m[N], s[N], mi[NXE];
 #pragma unroll
     for (int k = 0; k < N; ++k) mi[k] = lam[k];
-    exchange_x<T, PA, NXE>(mi, cx);
-    derivative<T, PA, NXE, NPE>(mi, qa, c, T(0), m);
+    exchange_x<V, PA, NXE>(mi, cx);
+    derivative<V, T, PA, NXE, NPE>(mi, qa, c, vzero<V>(), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = m[k]; mi[k] = fma(h2, m[k], lam[k]); }
-    exchange_x<T, PA, NXE>(mi, cx);
-    derivative<T, PA, NXE, NPE>(mi, qh, c, T(0), m);
+    exchange_x<V, PA, NXE>(mi, cx);
+    derivative<V, T, PA, NXE, NPE>(mi, qh, c, vzero<V>(), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h2, m[k], lam[k]); }
-    exchange_x<T, PA, NXE>(mi, cx);
-    derivative<T, PA, NXE, NPE>(mi, qh, c, T(0), m);
+    exchange_x<V, PA, NXE>(mi, cx);
+    derivative<V, T, PA, NXE, NPE>(mi, qh, c, vzero<V>(), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) { s[k] = fma(T(2), m[k], s[k]); mi[k] = fma(h, m[k], lam[k]); }
-    exchange_x<T, PA, NXE>(mi, cx);
-    derivative<T, PA, NXE, NPE>(mi, qb, c, T(0), m);
+    exchange_x<V, PA, NXE>(mi, cx);
+    derivative<V, T, PA, NXE, NPE>(mi, qb, c, vzero<V>(), m);
 #pragma unroll
     for (int k = 0; k < N; ++k) lam[k] = fma(h6, s[k] + m[k], lam[k]);
 #pragma unroll
@@ -422,7 +466,7 @@ PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   }
 
 #pragma unroll
-  for (int i = 0; i < N; ++i) a.lam[(long long)i * a.n_traj + p] = lam[i];
+  for (int i = 0; i < N; ++i) stv<V>(a.lam + (long long)i * a.n_traj + p, lam[i]);
 }
 
 struct NoDense {
