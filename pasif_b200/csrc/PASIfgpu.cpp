@@ -110,6 +110,10 @@ class GpuDriver {
     py::gil_scoped_release r;
     check(pasif_get_gradient_reduced_device(h, save, reinterpret_cast<void*>(device_ptr), (uint64_t)query("n_adj")));
   }
+  void reduceLastGradientDevice(uintptr_t device_ptr) {
+    py::gil_scoped_release r;
+    check(pasif_reduce_last_gradient_device(h, reinterpret_cast<void*>(device_ptr), (uint64_t)query("n_adj")));
+  }
 
  private:
   pasif_engine* h = nullptr;
@@ -178,6 +182,7 @@ PYBIND11_MODULE(PASIfgpu, m) {
       // additive
       .def("_getGradientReduced", &GpuDriver::getGradientReduced, py::arg("save") = 0)
       .def("_getGradientReducedDevice", &GpuDriver::getGradientReducedDevice, py::arg("device_ptr"), py::arg("save") = 0)
+      .def("_reduceLastGradientDevice", &GpuDriver::reduceLastGradientDevice, py::arg("device_ptr"))
       .def("_setOption", &GpuDriver::setOption, py::arg("key"), py::arg("value"))
       .def("_query", &GpuDriver::query, py::arg("key"));
 }

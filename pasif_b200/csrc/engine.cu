@@ -14,6 +14,7 @@
 #include <cuda_runtime.h>
 #include <dlfcn.h>
 #include <sys/stat.h>
+#include <unistd.h>
 #include <time.h>
 
 #include <algorithm>
@@ -21,6 +22,7 @@
 #include <cstring>
 #include <fstream>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -94,7 +96,7 @@ struct AotReg {
   __global__ void __launch_bounds__(PASIF_BLOCK) pasif_gfwd_f32x2_##TR(const pasif::FwdArgs<float> a) {         \
     pasif::forward_body<float, TR::Fwd, TR::Adj, 2>(a);                                                         \
   }                                                                                                             \
-  __global__ void __launch_bounds__(PASIF_BLOCK) pasif_bwd_f32x2_##TR(const pasif::BwdArgs<float> a) {          \
+  __global__ void __launch_bounds__(PASIF_BLOCK, 4) pasif_bwd_f32x2_##TR(const pasif::BwdArgs<float> a) {       \
     pasif::backward_body<float, TR::Adj, 2>(a);                                                                 \
   }                                                                                                             \
   AotReg reg_##TR(AotEntry{HASH, true, {nullptr, (const void*)pasif_gfwd_f64_##TR, (const void*)pasif_bwd_f64_##TR}, \
@@ -259,6 +261,10 @@ __global__ void tf32_mma_peak_kernel(float* out, int iters) {
 // ====================================================================================== NVRTC / driver entry points
 namespace {
 
+// process-global lazy state (NVRTC / driver entry points, the kernel header text) is initialised under one mutex: the
+// pybind shim releases the GIL while systems are allocated, so two engines may get here from two threads
+std::mutex g_init_mu;
+
 typedef struct _nvrtcProgram* nvrtcProgram;
 struct Nvrtc {
   void* lib = nullptr;
@@ -271,7 +277,8 @@ struct Nvrtc {
   int (*DestroyProgram)(nvrtcProgram*) = nullptr;
   int (*Version)(int*, int*) = nullptr;
   void load() {
-    if (lib) return;
+    std::lock_guard<std::mutex> lk(g_init_mu);
+    if (lib && Version) return;
     const char* names[] = {"libnvrtc.so.12", "libnvrtc.so", "/usr/local/cuda/lib64/libnvrtc.so.12",
                            "/usr/local/cuda/lib64/libnvrtc.so"};
     for (const char* n : names)
@@ -294,6 +301,8 @@ struct Nvrtc {
   }
 };
 Nvrtc g_nvrtc;
+// process-global lazy state (NVRTC / driver entry points, the kernel header text) is initialised under one mutex: the
+// pybind shim releases the GIL while systems are allocated, so two engines may get here from two threads
 
 struct DriverApi {
   bool ok = false;
@@ -303,6 +312,7 @@ struct DriverApi {
   CUresult (*LaunchKernel)(CUfunction, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, unsigned, CUstream,
                            void**, void**) = nullptr;
   void load() {
+    std::lock_guard<std::mutex> lk(g_init_mu);
     if (ok) return;
     auto get = [&](const char* name, void** fn) {
       cudaDriverEntryPointQueryResult q;
@@ -336,6 +346,7 @@ std::string read_file(const std::string& path) {
 
 std::string kernel_header_text() {
   static std::string cached;
+  std::lock_guard<std::mutex> lk(g_init_mu);
   if (!cached.empty()) return cached;
   std::vector<std::string> cand;
   if (const char* env = getenv("PASIF_B200_KERNEL_HEADER")) cand.push_back(env);
@@ -362,6 +373,11 @@ struct KernelHandle {
 // ====================================================================================== engine
 namespace {
 
+struct DevBuf;
+// buffer that may be given up when another allocation of the same engine runs out of device memory: the chunk
+// trajectories the exact schedule keeps in otherwise free HBM (d_tail).  Set by pasif_engine::use_device().
+thread_local DevBuf* tl_oom_victim = nullptr;
+
 struct DevBuf {
   void* p = nullptr;
   size_t cap = 0;
@@ -369,7 +385,13 @@ struct DevBuf {
     if (bytes <= cap) return;
     if (p) cudaFree(p);
     p = nullptr; cap = 0;
-    CUDA_CHECK(cudaMalloc(&p, bytes));
+    cudaError_t st = cudaMalloc(&p, bytes);
+    if (st == cudaErrorMemoryAllocation && tl_oom_victim && tl_oom_victim != this && tl_oom_victim->p) {
+      (void)cudaGetLastError();
+      tl_oom_victim->release();                  // kept chunk trajectories are a cache: the next gradient call re-sizes them
+      st = cudaMalloc(&p, bytes);
+    }
+    if (st != cudaSuccess) { p = nullptr; CUDA_CHECK(st); }
     cap = bytes;
   }
   void release() {
@@ -489,10 +511,11 @@ struct pasif_engine {
   void use_device() {
     if (host_only) throw std::runtime_error("this engine was created host-only (device = -1): no CUDA device to solve on");
     CUDA_CHECK(cudaSetDevice(device));
+    tl_oom_victim = &d_tail;
   }
 };
 
-static std::string g_create_error;
+static thread_local std::string g_create_error;   // pasif_create / the handle-less debug calls report per calling thread
 
 namespace {
 
@@ -525,7 +548,10 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
     else {
       s += "extern \"C\" __global__ void " + lb(minb_fwd) + " pasif_k_gfwd2(const pasif::FwdArgs<float> a) { pasif::forward_body<float, " +
            c.name + "::Fwd, " + c.name + "::Adj, 2>(a); }\n";
-      s += "extern \"C\" __global__ void " + lb(minb_bwd) + " pasif_k_bwd2(const pasif::BwdArgs<float> a) { pasif::backward_body<float, " +
+      // the adjoint pair kernel of the 12-state example Jacobian needs 150 registers uncapped = 3 CTAs per SM; capped at 128
+      // (4 CTAs) it runs 4 % faster (profiles/r02_probe_pair_variants.json).  Larger patterns keep the uncapped build.
+      const int est = c.adj.nc() + 8 * c.adj.N + 8 * (int)c.adj.nv.size() + 24;
+      s += "extern \"C\" __global__ void " + lb(minb_bwd > 0 ? minb_bwd : (est <= 180 ? 4 : 0)) + " pasif_k_bwd2(const pasif::BwdArgs<float> a) { pasif::backward_body<float, " +
            c.name + "::Adj, 2>(a); }\n";
     }
   }
@@ -541,10 +567,19 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
   return s;
 }
 
+// on-disk cache of the run-time specialised cubins.  Cubins are loaded as GPU code, so the directory must belong to this
+// user and be closed to others (0700); with neither PASIF_B200_CACHE nor HOME there is no cache (never a shared /tmp path).
 std::string cache_dir() {
-  if (const char* e = getenv("PASIF_B200_CACHE")) return e;
-  const char* home = getenv("HOME");
-  return std::string(home ? home : "/tmp") + "/.cache/pasif_b200";
+  std::string dir;
+  if (const char* e = getenv("PASIF_B200_CACHE")) dir = e;
+  else if (const char* home = getenv("HOME")) {
+    mkdir((std::string(home) + "/.cache").c_str(), 0755);
+    dir = std::string(home) + "/.cache/pasif_b200";
+  } else return std::string();
+  mkdir(dir.c_str(), 0700);
+  struct stat st;
+  if (stat(dir.c_str(), &st) != 0 || !S_ISDIR(st.st_mode) || st.st_uid != geteuid() || (st.st_mode & 077) != 0) return std::string();
+  return dir;
 }
 
 std::vector<char> jit_compile(pasif_engine& E, const std::string& src) {
@@ -556,7 +591,7 @@ std::vector<char> jit_compile(pasif_engine& E, const std::string& src) {
   g_nvrtc.Version(&vmaj, &vmin);
   const std::string key = detail::hex64(fnv1a(src + arch + std::to_string(vmaj * 100 + vmin)));
   const std::string dir = cache_dir(), path = dir + "/" + key + ".cubin";
-  {
+  if (!dir.empty()) {
     std::string blob = read_file(path);
     if (!blob.empty()) { ++E.jit_cache_hits; return std::vector<char>(blob.begin(), blob.end()); }
   }
@@ -579,14 +614,13 @@ std::vector<char> jit_compile(pasif_engine& E, const std::string& src) {
   g_nvrtc.GetCUBIN(prog, cubin.data());
   g_nvrtc.DestroyProgram(&prog);
   ++E.jit_compiles;
-  // best-effort disk cache
-  mkdir((std::string(getenv("HOME") ? getenv("HOME") : "/tmp") + "/.cache").c_str(), 0755);
-  mkdir(dir.c_str(), 0755);
-  std::ofstream f(path + ".tmp", std::ios::binary);
+  // best-effort disk cache (private directory only, see cache_dir)
+  if (dir.empty()) return cubin;
+  std::ofstream f(path + "." + std::to_string((long long)getpid()) + ".tmp", std::ios::binary);
   if (f) {
     f.write(cubin.data(), (std::streamsize)cubin.size());
     f.close();
-    rename((path + ".tmp").c_str(), path.c_str());
+    rename((path + "." + std::to_string((long long)getpid()) + ".tmp").c_str(), path.c_str());
   }
   return cubin;
 }
@@ -608,8 +642,9 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
   const int nmax = std::max(c.fwd.N, c.adj.N);
   if (nmax > 48 || c.fwd.nc() + c.adj.nc() > 2048)
     throw std::runtime_error("component " + c.name + " has " + std::to_string(nmax) + " coupled state variables / " +
-                             std::to_string(c.fwd.nc() + c.adj.nc()) + " coefficients: beyond the register-resident "
-                             "kernel's range (<= 48 variables); the shared-memory large-system path is not built yet");
+                             std::to_string(c.fwd.nc() + c.adj.nc()) + " coefficients: beyond the one-thread register "
+                             "kernel's range (<= 48 variables, <= 2048 coefficients) -- internal: such a component belongs to "
+                             "the lane-block / dense-operator / tile paths");
   g_drv.load();
   std::vector<char> cubin = jit_compile(E, jit_source(c, E.dtype, c.lanes > 1 ? E.lane_minb_fwd : E.jit_minb_fwd, c.lanes > 1 ? E.lane_minb_bwd : E.jit_minb_bwd));
   if (g_drv.ModuleLoadData(&dc.module, cubin.data()) != CUDA_SUCCESS)
@@ -698,6 +733,7 @@ bool is_large(const pasif_engine& E, const ClassData& c) {
 template <typename T>
 void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<DevClass>& out) {
   free_classes(out);
+  E.d_tail.release();                              // sized for the previous systems
   out.resize(cds.size());
   for (size_t i = 0; i < cds.size(); ++i) {
     DevClass& dc = out[i];
@@ -1007,8 +1043,12 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         if (ovl_) E.d_dense2.reserve(std::max<size_t>((size_t)chunk * NV * P, 1) * sizeof(T));   // count it before sizing
         size_t free_b = 0, total_b = 0;
         CUDA_CHECK(cudaMemGetInfo(&free_b, &total_b));
-        double budget = (double)(free_b + E.d_tail.cap) * 0.9;
-        if (E.tail_budget_gb > 0) budget = std::min(budget, E.tail_budget_gb * 1e9);
+        // automatic budget: 80 % of what is free, and never the last 6 GB -- torch / NCCL in the same process (bench.py,
+        // sharded.py) and the engine's own later buffers allocate from the same device; whatever is held here is also
+        // given back when another allocation of this engine fails (DevBuf::reserve) or on option trim
+        const double avail = (double)(free_b + E.d_tail.cap);
+        double budget = std::max(0.0, std::min(avail * 0.8, avail - 6e9));
+        if (E.tail_budget_gb > 0) budget = std::min(avail * 0.9, E.tail_budget_gb * 1e9);
         const double chunk_bytes = (double)chunk * NV * P * sizeof(T);
         const long long fit = (long long)(budget / chunk_bytes);
         sp_store = std::max<long long>(0, nsp - fit);
@@ -1164,6 +1204,7 @@ void load_exc(pasif_engine& E, const double* exc, uint32_t n_exc, uint32_t lengt
     for (auto* v : {&E.fwd_classes, &E.joint_classes})
       for (auto& c : *v) c.n_traj = (long long)c.h.n_inst * n_exc;
   }
+  if (E.have_exc && (n_exc != E.E || length != E.L)) E.d_tail.release();   // sized for the previous batch
   E.E = n_exc; E.L = length; E.sample_rate = sample_rate;
   if (!E.host_only) {
     // straight to the device, as the reference does (src/__GpuDriver.cu:343-381), but through pinned staging and
@@ -1409,11 +1450,21 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
   } else if (k == "lane_regs") {
     e->lane_regs = std::atoi(v.c_str());
   } else if (k == "large_threshold") {
-    e->large_threshold = std::atoi(v.c_str());
+    // one-thread register kernels hold at most 48 coupled variables; larger components go to the lane-block /
+    // dense-operator / tile paths whatever the option says
+    const int t = std::atoi(v.c_str());
+    if (t < 0 || t > 48) throw std::runtime_error("large_threshold must be in [0, 48]");
+    e->large_threshold = t;
   } else if (k == "overlap") {
     e->overlap = (v == "on" || v == "1");
   } else if (k == "profile") {
     e->profile = (v == "on" || v == "1");
+  } else if (k == "trim") {
+    // gives back device memory held between calls: the kept chunk trajectories and the work arrays of the solvers
+    if (!e->host_only) {
+      CUDA_CHECK(cudaSetDevice(e->device));
+      for (DevBuf* b : {&e->d_tail, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2}) b->release();
+    }
   } else if (k == "tail_budget_gb") {
     e->tail_budget_gb = (v == "auto") ? -1.0 : std::atof(v.c_str());
   } else if (k == "numsteps") {

@@ -151,6 +151,13 @@ class ShardedPASIf:
         """[lo, hi) of this rank's systems inside the reduced-gradient vector"""
         return self._adj_off, self._adj_off + self._adj_loc
 
+    def setExcitations(self, excitationSet, sampleRate):
+        """Replace the excitation set (every rank passes the FULL set; the rank keeps its block when the excitation
+        axis is split).  Same host -> device upload as the reference's `setExcitations` (PASIf.py:371-385)."""
+        e0, e1 = self._exc_range
+        exc = excitationSet[e0:e1] if (e0, e1) != (0, len(excitationSet)) else excitationSet
+        self.local._loadExcitationsSet(exc, sampleRate)
+
     # local shard, reference layout [e][i] over the rank's excitations / systems
     def getAmplitudes(self):
         return self.local.getAmplitudes()
@@ -187,6 +194,27 @@ class ShardedPASIf:
                 ev1.synchronize()
                 self.last_allreduce_ms = ev0.elapsed_time(ev1)
             return device_tensor
+        return self._reduce_host(d)
+
+    def getGradientAndReduced(self, device_tensor):
+        """ONE gradient evaluation, both results: the rank's un-reduced adjoint state [e][j] on the host (what the
+        reference's getGradient returns for the local shard) and the all-reduced, excitation-summed vector in
+        `device_tensor` (summed on the device from the same evaluation, then all-reduced in place)."""
+        import torch
+        d = _dist()
+        if device_tensor.numel() != self._adj_glob:
+            raise ValueError("device_tensor must hold %d values (global adjoint size)" % self._adj_glob)
+        local = self.local._getGradient(0)
+        device_tensor.zero_()
+        torch.cuda.current_stream(device_tensor.device).synchronize()
+        view = device_tensor[self._adj_off:self._adj_off + self._adj_loc]
+        self.local._reduceLastGradientDevice(view.data_ptr())
+        if d is not None and self.world > 1:
+            d.all_reduce(device_tensor)
+        return local, device_tensor
+
+    def _reduce_host(self, d):
+        off, n_loc = self._adj_off, self._adj_loc
         if hasattr(self.local, "_getGradientReduced"):
             loc = np.asarray(self.local._getGradientReduced(0), dtype=np.float64)
         else:                                      # driver without the additive reduced entry point
@@ -197,6 +225,11 @@ class ShardedPASIf:
         if d is not None and self.world > 1:
             import torch
             t = torch.from_numpy(full)
-            d.all_reduce(t)
-            full = t.numpy()
+            if d.get_backend() == "nccl":          # NCCL reduces device tensors only: stage through this rank's GPU
+                t = t.cuda()
+                d.all_reduce(t)
+                full = t.cpu().numpy()
+            else:
+                d.all_reduce(t)
+                full = t.numpy()
         return full

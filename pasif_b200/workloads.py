@@ -228,6 +228,23 @@ def jitter(system, rng, rel=0.1):
     return s
 
 
+def jitter_nonlinear(system, rng, rel=0.1):
+    """Parameter replica of ``system``: the linear operator (M, B, K) is kept bit for bit -- every replica shares K' --
+    while Gamma / Lambda / Psi / F values are scaled by independent U(1-rel, 1+rel) (BASELINE config 4: "excitation /
+    parameter replicas" of one large-DOF system).  Probe terms (coefficient exactly -1, p1' = x^2) are left alone."""
+    s = copy.deepcopy(system)
+
+    def jit(v):
+        v = np.asarray(v, dtype=np.float64)
+        return np.where(v == -1.0, v, v * rng.uniform(1.0 - rel, 1.0 + rel, size=v.shape))
+
+    for key in ("Gamma", "Lambda", "Psi"):
+        if key in s:
+            s[key] = (s[key][0], [float(x) for x in jit(s[key][1])], s[key][2])
+    s["F"] = jit(s["F"])
+    return s
+
+
 # --------------------------------------------------------------------------------------
 # excitations
 # --------------------------------------------------------------------------------------
