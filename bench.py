@@ -352,7 +352,9 @@ def make_job(ctx, w, a, *, presharded, strong):
     job.systems, job.jacs = systems, jacs
     job.exc = build_excitations(w)
     job.forward_only = bool(w.get("forward_only")) or jacs is None
-    opts = {"compat": a.compat, "tail_budget_gb": a.tail_budget_gb, "lanes": a.lanes}
+    # call_order=independent: every timed step is the same computation, the reference driver's FIRST call (the reference
+    # carries forward / adjoint state from one call into the next; reproduced by the engine's default)
+    opts = {"compat": a.compat, "tail_budget_gb": a.tail_budget_gb, "lanes": a.lanes, "call_order": "independent"}
     if a.lane_regs:
         opts["lane_regs"] = a.lane_regs
     if a.stage_parts:
@@ -701,6 +703,7 @@ def allreduce_check(ctx, w, a, job, strong, n_check=32):
         n = len(systems)
         q = frontend.make_frontend(capi.engine_class(w["dtype"]))(job.exc, 16000, 0)
         q._setOption("compat", a.compat)
+        q._setOption("call_order", "independent")
         q.setSystems(*wl.to_frontend_args(systems, mod))
         q.setJacobian(*wl.to_frontend_args(jacs, mod, with_psi=True))
         ref = np.asarray(q._getGradientReduced(0), dtype=np.float64)

@@ -13,6 +13,13 @@ repository holds no golden vectors for this path; its onl
 Two modes for the gradient:
   compat="reference"  literal schedule of `__GpuDriver::_getGradient` incl. quirks A1-A5 (SURVEY.md A.3)
   compat="clean"      exact checkpoints, all chunks, no aliasing: the mathematically intended sweep
+
+Call-order state (quirk A7, `call_order = "reference"`, the default): the driver's forward state `d_fwd_Q` is reset to the
+initial conditions only AFTER getAmplitudes / getTrajectory (src/__GpuDriver.cu:447, 482) and whenever the system is
+(re)allocated (:1183-1186); `_getGradient` starts its forward sweep from whatever it holds (:522-523) and leaves the end state
+of the last recomputed chunk behind (:565); the adjoint initial-condition buffer is overwritten with the running adjoint
+state (:743), so a second `_getGradient` without `setJacobian` continues from the previous result.  `call_order =
+"independent"` makes every call start from the initial conditions.
 """
 from __future__ import annotations
 
@@ -62,6 +69,9 @@ class PasifOracle:
         self.bwd = _System()
         self.interp = None
         self.numsteps = int(numsteps)
+        self.call_order = "reference"
+        self._q_cur = None                     # forward state left behind by the last _getGradient ([E][n]); None = IC
+        self._lam_cur = None                   # adjoint state carried into the next _getGradient ([E][n_adj]); None = IC
         self.load_excitations(excitations, sample_rate)
 
     # ---- __GpuDriver::_loadExcitationsSet / setTimesteps  (src/__GpuDriver.cu:343-381, 632-636)
@@ -93,9 +103,17 @@ class PasifOracle:
 
     def set_forward(self, K, G, L, P, F, IC):
         self._set(self.fwd, K, G, L, P, F, IC)
+        self._q_cur = None                     # allocateDeviceSystemStatesVector: d_fwd_Q <- IC (src/__GpuDriver.cu:1183-1186)
 
     def set_adjoint(self, K, G, L, P, F, IC):
         self._set(self.bwd, K, G, L, P, F, IC)
+        self._lam_cur = None                   # allocateDeviceAdjointStatesVector: d_bwd_QinitCond <- IC (:1363-1367)
+
+    def _take_q(self):
+        """forward state a sweep starts from: the driver's current one (quirk A7) or the initial conditions"""
+        if self.call_order == "reference" and self._q_cur is not None and self._q_cur.shape == (self.E, self.fwd.n):
+            return np.ascontiguousarray(self._q_cur, dtype=self.dtype)
+        return None
 
     # ---- __GpuDriver::_setInterpolationMatrix (src/__GpuDriver.cu:383-398)
     def set_interpolation(self, table_flat, window):
@@ -167,9 +185,11 @@ class PasifOracle:
 
     # ---- _getAmplitudes  (src/__GpuDriver.cu:416-461)
     def get_amplitudes(self):
-        Q = self._ic(self.fwd)
+        q0 = self._take_q()
+        Q = q0.copy() if q0 is not None else self._ic(self.fwd)
         for t in range(self.numsteps):
             Q = self._fwd_step(Q, t)
+        self._q_cur = None                                        # resetStatesVectors after the D2H copy (:447)
         return Q.reshape(-1).copy()
 
     # ---- _getTrajectory  (src/__GpuDriver.cu:463-500, save rule :669-687)
@@ -177,7 +197,9 @@ class PasifOracle:
         n = self.fwd.n * self.E
         n_slots = (n * self.numsteps) // save_steps // n if n else 0
         out = np.zeros((n_slots, self.E, self.fwd.n), dtype=self.dtype)
-        Q = self._ic(self.fwd)
+        q0 = self._take_q()
+        Q = q0.copy() if q0 is not None else self._ic(self.fwd)
+        self._q_cur = None                                        # resetStatesVectors (:482)
         k = 0
         for t in range(self.numsteps):
             Q = self._fwd_step(Q, t)
@@ -218,14 +240,16 @@ class PasifOracle:
         Nf = self.fwd.n
         slots = nsp + c - 2
         T = np.zeros((slots + 2, self.E, Nf), dtype=self.dtype)   # +2: A8 (one-past-the-end write) made defined
-        Q = self._ic(self.fwd)
+        carry = self.call_order == "reference"
+        q0 = self._take_q() if carry else None
+        Q = q0.copy() if q0 is not None else self._ic(self.fwd)   # A7: the sweep starts from the current d_fwd_Q (:522-523)
         k = 0
         for t in range(n):                                        # forward sweep, save AFTER step t when t % c == 0 (A1)
             Q = self._fwd_step(Q, t)
             if t % c == 0:
                 T[k] = Q
                 k += 1
-        lam = self._ic(self.bwd)
+        lam = self._lam_cur.copy() if (carry and self._lam_cur is not None and self._lam_cur.shape == (self.E, self.bwd.n)) else self._ic(self.bwd)   # A7 (:743, :1077)
         S = None                                                  # scratch slot frozen by the once-captured graph (A3)
         for sp in range(nsp - 1, 0, -1):                          # chunk 0 is never processed (A2)
             start = sp * c
@@ -251,6 +275,8 @@ class PasifOracle:
                 cur -= 1
             if sp == save:
                 break
+        if carry:
+            self._q_cur, self._lam_cur = Q.copy(), lam.copy()     # d_fwd_Q after the last recompute; d_bwd_QinitCond <- lambda
         return lam.reshape(-1).copy()
 
     def _gradient_clean(self):
@@ -278,12 +304,14 @@ class RecordingDriver:
     forwards solver calls to a PasifOracle.  `dtype` class attribute selects the emulated `reel`."""
     dtype = np.float64
     compat = "reference"
+    call_order = "reference"   # quirk A7 (module docstring); "independent": every call starts from the initial conditions
     oracle_cls = None      # default: PasifOracle (NumPy); pasif_oracle_c.CRecordingDriver swaps in the C oracle
 
     def __init__(self, excitationSet_, sampleRate_, numsteps_, dCompute_=False, dSystem_=False, dSolver_=False, GPUId_=0):
         self.rec = {}
         cls = self.oracle_cls or PasifOracle
         self._oracle = cls(np.asarray(excitationSet_, dtype=np.float64), sampleRate_, numsteps_, self.dtype)
+        self._oracle.call_order = self.call_order
         self._psi_f = None
         self._psi_b = None
 
@@ -341,6 +369,14 @@ class RecordingDriver:
 
     def _setModulationBuffer(self, modulationBuffer_):
         self.rec["modulation"] = np.array(modulationBuffer_, np.float64)     # never read by any kernel in the reference
+
+    def _setOption(self, key, value):
+        if key == "compat":
+            self.compat = value
+        elif key == "call_order":
+            self.call_order = self._oracle.call_order = value
+        else:
+            raise KeyError(key)
 
     def _getAmplitudes(self):
         return [float(x) for x in self._oracle.get_amplitudes()]

@@ -85,6 +85,8 @@ class COracle(PasifOracle):
 
     def _forward(self, save_steps, n_slots):
         keep = []
+        q0 = self._take_q()                      # call-order state (quirk A7), None = initial conditions
+        self._q_cur = None                       # getAmplitudes / getTrajectory reset the state afterwards
         s, c = self._pack_sys(self.fwd, keep), self._pack_ctx(keep)
         rp = C.POINTER(self._real)
         out = np.zeros((self.E, self.fwd.n), dtype=self.dtype)
@@ -92,7 +94,8 @@ class COracle(PasifOracle):
         fn = getattr(_lib(), "oracle_forward_" + self._sfx)
         fn.restype = C.c_int
         rc = fn(C.byref(s), C.byref(c), C.c_long(self.numsteps), out.ctypes.data_as(rp), C.c_long(save_steps),
-                traj.ctypes.data_as(rp) if traj is not None else None, C.c_long(n_slots), C.c_int(self.threads))
+                traj.ctypes.data_as(rp) if traj is not None else None, C.c_long(n_slots), C.c_int(self.threads),
+                q0.ctypes.data_as(rp) if q0 is not None else None)
         if rc:
             raise MemoryError("oracle_forward")
         return out, traj
@@ -112,12 +115,20 @@ class COracle(PasifOracle):
         rp = C.POINTER(self._real)
         nsp, chunk, last = self.schedule() if self.numsteps > 0 else (0, 1, 1)
         out = np.zeros((self.E, self.bwd.n), dtype=self.dtype)
+        carry = compat == "reference" and self.call_order == "reference"
+        q0 = self._take_q() if carry else None
+        lam0 = self._lam_cur if (carry and self._lam_cur is not None and self._lam_cur.shape == (self.E, self.bwd.n)) else None
+        q_end = np.zeros((self.E, self.fwd.n), dtype=self.dtype) if carry else None
         fn = getattr(_lib(), "oracle_gradient_" + self._sfx)
         fn.restype = C.c_int
         rc = fn(C.byref(f), C.byref(b), C.byref(c), C.c_long(self.numsteps), C.c_int(0 if compat == "reference" else 1),
-                C.c_long(nsp), C.c_long(chunk), C.c_long(last), C.c_long(save), out.ctypes.data_as(rp), C.c_int(self.threads))
+                C.c_long(nsp), C.c_long(chunk), C.c_long(last), C.c_long(save), out.ctypes.data_as(rp), C.c_int(self.threads),
+                q0.ctypes.data_as(rp) if q0 is not None else None, lam0.ctypes.data_as(rp) if lam0 is not None else None,
+                q_end.ctypes.data_as(rp) if q_end is not None else None)
         if rc:
             raise MemoryError("oracle_gradient")
+        if carry:
+            self._q_cur, self._lam_cur = q_end, out.copy()
         return out.reshape(-1)
 
 

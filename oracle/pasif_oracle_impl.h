@@ -80,9 +80,12 @@ static void NAME(bwd_step)(const NAME(sys_t)* b, const NAME(ctx_t)* c, REAL* lam
   for (int i = 0; i < n; ++i) lam[i] += c->h6 * (m1[i] + 2 * m2[i] + 2 * m3[i] + m4[i]);
 }
 
-/* getAmplitudes / getTrajectory: out_final [E][n]; traj [slot][E][n] (may be NULL) */
+/* getAmplitudes / getTrajectory: out_final [E][n]; traj [slot][E][n] (may be NULL).
+ * q0 [E][n] or NULL: the forward state the driver currently holds -- the reference starts every sweep from d_fwd_Q as it
+ * stands and resets it to the initial conditions only AFTER getAmplitudes / getTrajectory (src/__GpuDriver.cu:428-447,
+ * 480-484); NULL = initial conditions. */
 int NAME(oracle_forward)(const NAME(sys_t)* s, const NAME(ctx_t)* c, long numsteps, REAL* out_final, long save_steps,
-                         REAL* traj, long n_slots, int threads) {
+                         REAL* traj, long n_slots, int threads, const REAL* q0) {
   const int n = s->n;
   int err = 0;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
@@ -90,7 +93,7 @@ int NAME(oracle_forward)(const NAME(sys_t)* s, const NAME(ctx_t)* c, long numste
     REAL* Q = (REAL*)malloc(sizeof(REAL) * 6 * (size_t)(n > 0 ? n : 1));
     if (!Q) { err = 1; continue; }
     REAL* w = Q + n;
-    memcpy(Q, s->ic, sizeof(REAL) * n);
+    memcpy(Q, q0 ? q0 + (size_t)e * n : s->ic, sizeof(REAL) * n);
     long slot = 0;
     for (long t = 0; t < numsteps; ++t) {
       NAME(fwd_step)(s, c, e, t, Q, w);
@@ -106,9 +109,13 @@ int NAME(oracle_forward)(const NAME(sys_t)* s, const NAME(ctx_t)* c, long numste
 }
 
 /* getGradient.  compat 0 = literal reference schedule (quirks A1-A5), 1 = exact ("clean") sweep.
- * nsp / chunk / last are computed by the caller exactly as src/__GpuDriver.cu:506-508.  out [E][n_adj]. */
+ * nsp / chunk / last are computed by the caller exactly as src/__GpuDriver.cu:506-508.  out [E][n_adj].
+ * Call-order state (quirk A7): q0 [E][nf] / lam0 [E][na] = forward state / adjoint state the driver currently holds (NULL =
+ * initial conditions); q_end [E][nf] (may be NULL) receives the forward state the call leaves behind in d_fwd_Q: the end of
+ * the last recomputed chunk (src/__GpuDriver.cu:565), or of the sweep when no chunk is processed. */
 int NAME(oracle_gradient)(const NAME(sys_t)* f, const NAME(sys_t)* b, const NAME(ctx_t)* c, long numsteps, int compat,
-                          long nsp, long chunk, long last, long save, REAL* out, int threads) {
+                          long nsp, long chunk, long last, long save, REAL* out, int threads, const REAL* q0,
+                          const REAL* lam0, REAL* q_end) {
   const int nf = f->n, na = b->n;
   int err = 0;
 #pragma omp parallel for schedule(dynamic, 1) num_threads(threads)
@@ -121,8 +128,8 @@ int NAME(oracle_gradient)(const NAME(sys_t)* f, const NAME(sys_t)* b, const NAME
     REAL* lam = wf + 5 * nf;
     REAL* wb = lam + na;
     REAL* qa = wb + 5 * na; REAL* qh = qa + nf; REAL* qb = qh + nf;
-    memcpy(Q, f->ic, sizeof(REAL) * nf);
-    memcpy(lam, b->ic, sizeof(REAL) * na);
+    memcpy(Q, q0 ? q0 + (size_t)e * nf : f->ic, sizeof(REAL) * nf);
+    memcpy(lam, lam0 ? lam0 + (size_t)e * na : b->ic, sizeof(REAL) * na);
     if (compat != 0) {
       /* exact sweep: store every state, adjoint step k uses q_{k+1}, (q_{k+1}+q_k)/2, q_k for k = n-1 .. 0 */
       memcpy(T, Q, sizeof(REAL) * nf);
@@ -166,6 +173,7 @@ int NAME(oracle_gradient)(const NAME(sys_t)* f, const NAME(sys_t)* b, const NAME
       }
     }
     memcpy(out + (size_t)e * na, lam, sizeof(REAL) * na);
+    if (q_end) memcpy(q_end + (size_t)e * nf, Q, sizeof(REAL) * nf);
     free(T); free(Q);
   }
   return err;

@@ -25,6 +25,9 @@ def main():
     ap.add_argument("--excitations", type=int, default=64)
     ap.add_argument("--steps", type=int, default=20000)
     ap.add_argument("--exc-seed", type=int, default=2)
+    ap.add_argument("--forward-only", action="store_true",
+                    help="no Jacobian / gradient: the only way to time the reference on more than 2 systems (its front end cannot "
+                         "assemble more Jacobians); above nnz 128 its results are invalid (quirk F4), its time is still its time")
     a = ap.parse_args()
     sys.path.insert(0, os.path.join(REF, a.prec))
     sys.path.insert(0, REF)
@@ -39,11 +42,20 @@ def main():
     stdout = os.dup(1)
     os.dup2(2, 1)                    # the reference prints "[Info] ..." lines on stdout
     p = ref.PASIf(exc, 16000, 0)
+    t0 = time.time()
     p.setSystems(*wl.to_frontend_args(systems, ref))
+    t_set = time.time() - t0
     p.getAmplitudes()                # warm-up (graph capture, allocations)
     t0 = time.time()
     p.getAmplitudes()
     t_f = time.time() - t0
+    if a.forward_only:
+        sys.stdout.flush()
+        os.dup2(stdout, 1)
+        print(json.dumps({"prec": a.prec, "systems": a.systems, "excitations": a.excitations, "steps": a.steps, "forward_s": t_f,
+                          "setSystems_s": t_set, "forward_system_steps_per_s": a.systems * a.excitations * a.steps / t_f,
+                          "results_valid": bool(a.systems * 5 <= 128)}))
+        return
     p.setJacobian(*wl.to_frontend_args(jacs, ref, with_psi=True))
     t0 = time.time()
     p.getGradient()

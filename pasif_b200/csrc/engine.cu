@@ -176,6 +176,21 @@ __global__ void scatter_user_kernel(const T* __restrict__ st, const int* __restr
   if (g >= 0) out[(long long)e * n_glob + g] = st[idx];
 }
 
+// user layout [e][n_glob] -> class layout [N][n_traj] (the inverse of scatter_user_kernel); padding slots take the class's
+// initial condition.  Used for the call-order state (a sweep that starts from the state a previous call left behind).
+template <typename T>
+__global__ void gather_user_kernel(const T* __restrict__ user, const int* __restrict__ varmap, const T* __restrict__ ic,
+                                   T* __restrict__ st, int N, int n_inst, int E, int n_traj, int n_glob, int G) {
+  const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (long long)N * n_traj) return;
+  const int i = (int)(idx / n_traj);
+  const int p = (int)(idx - (long long)i * n_traj);
+  const int lane = p % G, traj = p / G;
+  const int e = traj % E, inst = (traj / E) * G + lane;
+  const int g = varmap[(long long)i * n_inst + inst];
+  st[idx] = g >= 0 ? user[(long long)e * n_glob + g] : ic[(long long)i * n_inst + inst];
+}
+
 // out[j] = sum_e in[e][j]: each warp owns 32 consecutive columns while striding over e, the 32 row-partials of a
 // column are then transposed through shared memory and folded with warp shuffles (fixed order -> deterministic).
 template <typename T>
@@ -427,6 +442,8 @@ struct DevClass {
   DevBuf coef, ic, varmap, coef_adj, ic_adj, varmap_adj;
   KernelHandle k_fwd, k_gfwd, k_bwd;
   KernelHandle k_fwd2, k_gfwd2, k_bwd2;         // fp32 one-thread classes: two trajectories per thread (packed FFMA2)
+  DevBuf lam_carry;                             // call_order=reference: adjoint state the last gradient call left behind [NA][n_traj]
+  bool lam_dirty = false;
   CUmodule module = nullptr;
   long long n_traj = 0;
 };
@@ -455,6 +472,15 @@ struct pasif_engine {
   DevBuf d_raw, d_exc, d_user, d_traj, d_ckpt, d_dense, d_dense2, d_lam, d_red;   // d_raw: excitations as handed over, [E][L] doubles
   PinnedBuf h_stage;                               // 2 slots of kStageSlot bytes
   cudaEvent_t ev_stage[2] = {nullptr, nullptr};
+  // Call-order state of the reference driver (option call_order = reference | independent).  The reference
+  // resets its forward state d_fwd_Q to the initial conditions only AFTER getAmplitudes / getTrajectory and when the system
+  // is allocated (src/__GpuDriver.cu:447, 482, 1183-1186); _getGradient starts from whatever it holds (:522-523) and leaves
+  // the end of its last recomputed chunk behind (:565), and the adjoint initial-condition buffer is overwritten with the
+  // running adjoint state (:743).  Reproduced for the register / lane-block classes in compat=reference: d_fwd_cur holds the
+  // forward state a previous gradient call left behind (user layout), DevClass::lam_carry the adjoint state.
+  bool call_order_ref = true;
+  bool fwd_dirty = false;
+  DevBuf d_fwd_cur, d_q0, d_qend;                  // [E][N_glob] | class-layout start state | class-layout end state
   int d_user_kind = 0;                             // what d_user holds: 0 nothing | 1 amplitudes [E][N] | 2 adjoint state [E][N_adj]
   double last_h2d_ms = 0, last_d2h_ms = 0;         // host wall time of the last staged upload / download
   long long exc_rows = 0;
@@ -714,6 +740,7 @@ void free_classes(std::vector<DevClass>& v) {
   for (auto& c : v) {
     c.coef.release(); c.ic.release(); c.varmap.release();
     c.coef_adj.release(); c.ic_adj.release(); c.varmap_adj.release();
+    c.lam_carry.release();
     c.large.reset();
     if (c.module && g_drv.ok) g_drv.ModuleUnload(c.module);
   }
@@ -781,6 +808,7 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
 double eps_of(const pasif_engine& E) { return E.dtype == PASIF_F32 ? 1.1920928955078125e-07 : 2.220446049250313e-16; }
 
 void analyze_fwd(pasif_engine& E) {
+  E.fwd_dirty = false;                             // allocateDeviceSystemStatesVector: d_fwd_Q <- initial conditions
   auto cds = analyze_forward(E.fwd, eps_of(E), E.dtype == PASIF_F32);
   if (E.dtype == PASIF_F32) build_classes<float>(E, std::move(cds), E.fwd_classes);
   else build_classes<double>(E, std::move(cds), E.fwd_classes);
@@ -938,6 +966,19 @@ void download(pasif_engine& E, const void* dev, double* out, uint64_t n) {
   E.last_d2h_ms = wall_ms() - t0;
 }
 
+// class-layout copy [N][n_traj] of the forward state a previous gradient call left behind (E.d_fwd_cur, user layout);
+// stream-ordered, so consecutive classes may share the scratch buffer
+template <typename T>
+const T* gather_start_state(pasif_engine& E, const DevClass& c) {
+  const long long tot = (long long)c.h.fwd.N * c.n_traj;
+  E.d_q0.reserve((size_t)std::max<long long>(tot, 1) * sizeof(T));
+  gather_user_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>(
+      (const T*)E.d_fwd_cur.p, (const int*)c.varmap.p, (const T*)c.ic.p, (T*)E.d_q0.p, c.h.fwd.N, c.h.n_inst, (int)E.E,
+      (int)c.n_traj, (int)E.fwd.n, c.h.lanes);
+  ++E.last_launches;
+  return (const T*)E.d_q0.p;
+}
+
 // ---- getAmplitudes / getTrajectory
 template <typename T>
 void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n_out, bool trajectory) {
@@ -961,6 +1002,7 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
     pasif::FwdArgs<T> a;
     fill_common<T>(E, c, a);
     a.t0 = 0; a.t1 = (int)E.numsteps;
+    if (E.fwd_dirty) a.q_in = gather_start_state<T>(E, c);      // quirk A7: the sweep starts from the current forward state
     if (trajectory) {
       a.save_ptr = (T*)E.d_traj.p; a.save_every = (int)save_steps; a.save_phase = 0; a.save_layout = 1;
       a.save_slots = (int)n_slots;
@@ -971,6 +1013,7 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
     else launch(E, c.k_fwd, c.n_traj, a, 0, nullptr, c.h.lanes);
   }
   end_timing(E);
+  E.fwd_dirty = false;                             // resetStatesVectors after getAmplitudes / getTrajectory (:447, :482)
   if (!trajectory) E.d_user_kind = 1;
   download<T>(E, trajectory ? E.d_traj.p : E.d_user.p, out, trajectory ? n_slots * width : width);
 }
@@ -1009,11 +1052,22 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     const long long PT = pairs ? P / 2 : P;        // threads
     if (pairs) ++E.pair_launches;
     E.d_lam.reserve((size_t)NA * P * sizeof(T));
-    {
+    // call-order state (quirk A7), literal schedule only: the adjoint state continues from what the previous call left in
+    // the initial-condition buffer, the forward sweep from the current forward state
+    const bool carry = E.call_order_ref && !E.compat_clean;
+    if (carry && c.lam_dirty && c.lam_carry.cap >= (size_t)NA * P * sizeof(T)) {
+      CUDA_CHECK(cudaMemcpyAsync(E.d_lam.p, c.lam_carry.p, (size_t)NA * P * sizeof(T), cudaMemcpyDeviceToDevice, E.stream));
+    } else {
       const long long tot = (long long)NA * P;
       init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
           (const T*)c.ic_adj.p, (T*)E.d_lam.p, NA, c.h.n_inst, (int)E.E, (int)P, c.h.lanes);
       ++E.last_launches;
+    }
+    const T* q_start = (carry && E.fwd_dirty) ? gather_start_state<T>(E, c) : nullptr;
+    T* q_end = nullptr;                              // class-layout forward state this call leaves behind
+    if (carry) {
+      E.d_qend.reserve(std::max<size_t>((size_t)NF * P, 1) * sizeof(T));
+      q_end = (T*)E.d_qend.p;
     }
     if (n > 0) {
       long long nsp, chunk, S_global = -1;
@@ -1064,6 +1118,8 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
         a.save_ptr = ckpt; a.save_every = (int)chunk; a.save_layout = 0; a.save_slots = (int)nsp;
         if (!E.compat_clean) {
           a.save_phase = 0;                        // slot j <- state AFTER step j*c (quirk A1)
+          a.q_in = q_start;                        // nullptr: initial conditions
+          a.q_out = q_end;                         // what stays in d_fwd_Q if no chunk is recomputed afterwards
           launch(E, k_gfwd, PT, a, 1, nullptr, c.h.lanes);
         } else {
           a.save_phase = 1;                        // slot j <- state BEFORE step j*c; slot 0 = initial condition
@@ -1108,6 +1164,8 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
           a.q_in = ckpt + (size_t)sp * slot_elems;
           a.t0 = (int)start; a.t1 = (int)end;
           a.dense_ptr = dense_buf[buf];
+          // the last chunk this call recomputes leaves its end state in d_fwd_Q (src/__GpuDriver.cu:565)
+          if (q_end && (sp == first || sp == (long long)save)) a.q_out = q_end;
           launch(E, k_gfwd, PT, a, 1, E.stream, c.h.lanes);
         }
         if (ovl) {                                 // (for a stored chunk: orders the adjoint stream after the sweep)
@@ -1138,6 +1196,16 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     scatter_user_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
         (const T*)E.d_lam.p, (const int*)c.varmap_adj.p, d_user_out, NA, c.h.n_inst, (int)E.E, (int)P, (int)E.bwd.n, c.h.lanes);
     ++E.last_launches;
+    if (carry) {
+      // d_bwd_QinitCond <- running adjoint state (src/__GpuDriver.cu:743); d_fwd_Q keeps the last recomputed state
+      c.lam_carry.reserve((size_t)NA * P * sizeof(T));
+      CUDA_CHECK(cudaMemcpyAsync(c.lam_carry.p, E.d_lam.p, (size_t)NA * P * sizeof(T), cudaMemcpyDeviceToDevice, E.stream));
+      c.lam_dirty = true;
+      const long long ftot = (long long)NF * P;
+      scatter_user_kernel<T><<<(unsigned)((ftot + threads - 1) / threads), threads, 0, E.stream>>>(
+          (const T*)q_end, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, NF, c.h.n_inst, (int)E.E, (int)P, (int)E.fwd.n, c.h.lanes);
+      ++E.last_launches;
+    }
   }
 }
 
@@ -1152,7 +1220,26 @@ void gradient_entry(pasif_engine& E, uint32_t save, double* out, uint64_t n_out,
   if (reduced && (out || dev_out) && n_out != E.bwd.n) throw std::runtime_error("reduced gradient buffer must hold N_adj values");
   E.d_user.reserve(std::max<uint64_t>(width, 1) * sizeof(T));
   begin_timing(E);
+  const bool carry = E.call_order_ref && !E.compat_clean;
+  if (carry) {
+    // forward state in the user layout: variables of components no adjoint variable depends on are not integrated by the
+    // gradient path and keep their initial conditions
+    const uint64_t fw = (uint64_t)E.fwd.n * E.E;
+    E.d_fwd_cur.reserve(std::max<uint64_t>(fw, 1) * sizeof(T));
+    if (!E.fwd_dirty)
+      for (DevClass& c : E.fwd_classes) {
+        if (c.large) continue;
+        const long long tot = (long long)c.h.fwd.N * c.n_traj;
+        E.d_q0.reserve((size_t)std::max<long long>(tot, 1) * sizeof(T));
+        init_state_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>((const T*)c.ic.p, (T*)E.d_q0.p, c.h.fwd.N, c.h.n_inst,
+                                                                                   (int)E.E, (int)c.n_traj, c.h.lanes);
+        scatter_user_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>(
+            (const T*)E.d_q0.p, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, c.h.fwd.N, c.h.n_inst, (int)E.E, (int)c.n_traj, (int)E.fwd.n, c.h.lanes);
+        E.last_launches += 2;
+      }
+  }
   solve_gradient<T>(E, save, (T*)E.d_user.p);
+  if (carry) E.fwd_dirty = true;
   T* red = nullptr;
   if (reduced) {
     E.d_red.reserve(std::max<uint64_t>(E.bwd.n, 1) * sizeof(T));
@@ -1205,6 +1292,10 @@ void load_exc(pasif_engine& E, const double* exc, uint32_t n_exc, uint32_t lengt
       for (auto& c : *v) c.n_traj = (long long)c.h.n_inst * n_exc;
   }
   if (E.have_exc && (n_exc != E.E || length != E.L)) E.d_tail.release();   // sized for the previous batch
+  if (E.have_exc && n_exc != E.E) {                // a different batch: nothing a previous call left behind applies to it
+    E.fwd_dirty = false;
+    for (auto& c : E.joint_classes) c.lam_dirty = false;
+  }
   E.E = n_exc; E.L = length; E.sample_rate = sample_rate;
   if (!E.host_only) {
     // straight to the device, as the reference does (src/__GpuDriver.cu:343-381), but through pinned staging and
@@ -1283,7 +1374,8 @@ void pasif_destroy(pasif_engine* e) {
     cudaSetDevice(e->device);
     free_classes(e->fwd_classes);
     free_classes(e->joint_classes);
-    for (DevBuf* b : {&e->d_tail, &e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red}) b->release();
+    for (DevBuf* b : {&e->d_tail, &e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red,
+                      &e->d_fwd_cur, &e->d_q0, &e->d_qend}) b->release();
     for (int i = 0; i < 2; ++i) {
       if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
@@ -1385,6 +1477,13 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     if (v == "reference") e->compat_clean = false;
     else if (v == "clean") e->compat_clean = true;
     else throw std::runtime_error("compat must be 'reference' or 'clean'");
+  } else if (k == "call_order") {
+    // "reference": repeated solver calls behave like the reference driver (quirk A7: _getGradient continues from the forward /
+    // adjoint state the previous call left behind; getAmplitudes / getTrajectory reset the forward state afterwards);
+    // "independent": every call starts from the initial conditions
+    if (v == "reference") e->call_order_ref = true;
+    else if (v == "independent") { e->call_order_ref = false; e->fwd_dirty = false; for (auto& c : e->joint_classes) c.lam_dirty = false; }
+    else throw std::runtime_error("call_order must be 'reference' or 'independent'");
   } else if (k == "jit") {
     e->jit_on = (v == "on" || v == "1");
   } else if (k == "block") {

@@ -363,7 +363,45 @@ def golden_case(name):
         return dict(systems=[ex1dof_system(k=400.0, b=2.0)], jacobians=[ex1dof_jacobian()],
                     excitations=sine_excitations([5., 11.], 6000, sr), sample_rate=sr, numsteps=4900,
                     interp=None, traj_save_steps=None)
+    if name == "calls_ex1dof_short":           # call-order sequence (run_call_sequence), two excitations
+        return dict(golden_case("ex1dof_short"), traj_save_steps=None)
+    if name == "calls_ex1dof_e1":              # ... one excitation, so the returned adjoint state can re-seed setJacobian
+        return dict(systems=[ex1dof_system(k=400.0, b=2.0)], jacobians=[ex1dof_jacobian()],
+                    excitations=sine_excitations([5.], 6000, sr), sample_rate=sr, numsteps=5000,
+                    interp=None, traj_save_steps=None)
     raise KeyError(name)
+
+
+# call-order fixtures: what the reference returns when its solvers are called repeatedly; the last
+# three calls re-seed the adjoint from the returned state like examples/FullInterfaceTesting_1dof.py:233-237
+CALL_ORDER_CASES = ("calls_ex1dof_short", "calls_ex1dof_e1")
+
+
+def run_call_sequence(p, case, mod):
+    """Drive front end `p` (already holding the case's systems) through the call-order sequence; -> dict of outputs.
+    a0 amplitudes | setJacobian | g1, g2 two gradients in a row | a1, a2 two amplitude calls | (one excitation only)
+    setJacobian again, then three `_getGradient(save)` calls, each followed by setJacobian with the returned state as the
+    adjoint initial condition."""
+    import math
+    out = {}
+    jac = lambda: to_frontend_args(case["jacobians"], mod, with_psi=True)  # noqa: E731
+    out["a0"] = np.asarray(p.getAmplitudes(), dtype=np.float64)
+    p.setJacobian(*jac())
+    out["g1"] = np.asarray(p._getGradient(0), dtype=np.float64)
+    out["g2"] = np.asarray(p._getGradient(0), dtype=np.float64)
+    out["a1"] = np.asarray(p.getAmplitudes(), dtype=np.float64)
+    out["a2"] = np.asarray(p.getAmplitudes(), dtype=np.float64)
+    if len(case["excitations"]) == 1 and len(case["systems"]) == 1:
+        p.setJacobian(*jac())
+        n = case["numsteps"] or len(case["excitations"][0])
+        nsp = int(math.sqrt(n))
+        for i, save in enumerate((nsp - 1, nsp - 2, nsp - 3)):
+            g = np.asarray(p._getGradient(save), dtype=np.float64)
+            out[f"s{i}"] = g
+            j = copy.deepcopy(case["jacobians"][0])
+            j["IC"] = g.copy()
+            p.setJacobian(*to_frontend_args([j], mod, with_psi=True))
+    return out
 
 
 GOLDEN_CASES = ("ex1dof", "duffing8", "fit8_e16", "fit8_c2", "fit8x2_jit", "mixed2",

@@ -47,6 +47,13 @@ def run_case(name, prec, out_dir):
     if case["interp"] is not None:
         table, W = case["interp"]
         p.setInterpolationMatrix([np.array(r) for r in table])
+    if name in wl.CALL_ORDER_CASES:                  # repeated solver calls on one driver (quirk A7)
+        out = wl.run_call_sequence(p, case, ref)
+        meta["gpu"] = subprocess.check_output(["nvidia-smi", "--query-gpu=name,driver_version", "--format=csv,noheader"], text=True).strip()
+        meta["reference_commit"] = "5fd9fd1"
+        np.savez_compressed(os.path.join(out_dir, f"ref_{name}_{prec}.npz"), meta=json.dumps(meta), **out)
+        print("WROTE", name, prec, sorted(out))
+        return
     out["amplitudes"] = np.array(timed("getAmplitudes", p.getAmplitudes), dtype=np.float64)
     out["amplitudes_2nd"] = np.array(timed("getAmplitudes_2nd", p.getAmplitudes), dtype=np.float64)
     if case["traj_save_steps"]:
@@ -76,8 +83,8 @@ def main():
         run_case(a.case, a.prec, a.out)
         return
     sys.path.insert(0, ROOT)
-    from pasif_b200.workloads import GOLDEN_CASES
-    cases = a.cases.split(",") if a.cases else GOLDEN_CASES
+    from pasif_b200.workloads import GOLDEN_CASES, CALL_ORDER_CASES
+    cases = a.cases.split(",") if a.cases else GOLDEN_CASES + CALL_ORDER_CASES
     rc = 0
     for prec in ("f64", "f32"):
         for name in cases:

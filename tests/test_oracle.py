@@ -60,6 +60,24 @@ def test_c_oracle_matches_reference_golden_config2_subset():
     assert col_err(out["gradient"], z["gradient"][:64 * 12], 12) < 1e-12
 
 
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("base", [po.RecordingDriver, CRecordingDriver])
+def test_oracle_call_order_matches_reference(base, prec):
+    """Call-order state against a fixture of the unmodified reference: amplitudes, two gradients in a row,
+    amplitudes twice more on one driver (pasif_b200.workloads.run_call_sequence)."""
+    from conftest import frontend_mod
+    from pasif_b200 import frontend
+    z = golden("calls_ex1dof_short", prec)
+    case = wl.golden_case("calls_ex1dof_short")
+    p = frontend.make_frontend(_driver(base, prec))([np.array(r) for r in case["excitations"]], case["sample_rate"], case["numsteps"])
+    p.setSystems(*wl.to_frontend_args(case["systems"], frontend_mod))
+    out = wl.run_call_sequence(p, case, frontend_mod)
+    assert not np.array_equal(z["g1"], z["g2"]) and not np.array_equal(z["a0"], z["a1"])
+    for k in ("a0", "g1", "g2", "a1", "a2"):
+        assert rel_err(out[k], z[k]) < TOL[prec], k
+        assert col_err(out[k], z[k], 4 if k[0] == "a" else 6) < (1e-12 if prec == "f64" else 5e-5), k
+
+
 def _random_case(seed, n_sys=2, L=400):
     rng = np.random.default_rng(seed)
     return dict(systems=[wl.jitter(wl.fit8_system(), rng, 0.3) for _ in range(n_sys)],

@@ -4,11 +4,14 @@
   * size-independent properties at larger sizes (replica equality, linearity, reduction consistency, idempotence).
 Tolerances (north star: <= 1e-12 relative in double, <= 1e-5 relative in float):
   fp64  every state variable: max_e |a - b| <= 1e-12 * max_e |b|                     (col_err, per variable)
-  fp32  whole output vector:  max |a - b|   <= 1e-5 (forward) / 5e-5 (adjoint) * max |b|   (rel_err)
-        and per variable <= 2e-3: a variable that ends near a zero crossing of its oscillation carries the fp32
-        round-off of up to 78 001 steps relative to a small final value; two fp32 implementations that differ only in
-        rounding order (the reference's GPU build vs the C restatement) differ by the same amount -- asserted in
-        test_fp32_deviation_is_rounding_noise."""
+  fp32  whole output vector:  max |a - b|   <= 1e-5 * max |b|, forward AND adjoint    (rel_err)
+        and per variable <= 5e-4.  Measured (profiles/PARITY.md, every fixture of the unmodified reference): the CUDA path
+        is within 3.6e-6 (forward) / 7.7e-10 (adjoint) of the reference's fp32 output on the whole vector.  Per variable
+        the worst case is 1.5e-4 (fit8x2_jit amplitudes: a variable that ends near a zero crossing of its oscillation
+        carries the fp32 round-off of 20 000 steps relative to a small final value) -- and the literal C restatement of
+        the reference, which differs from the reference's GPU build only in rounding order, is exactly as far from it
+        (1.5e-4), while the reference's own fp32 build is up to 1.7e-3 per variable from its fp64 build.  So 1e-5 per
+        VARIABLE is below what two fp32 builds of the same arithmetic can agree on; it holds on the whole vector."""
 import os
 import sys
 
@@ -22,8 +25,8 @@ from pasif_oracle_c import CRecordingDriver
 pytestmark = pytest.mark.gpu
 
 TOL_FWD = {"f64": 1e-12, "f32": 1e-5}
-TOL_ADJ = {"f64": 1e-12, "f32": 5e-5}
-TOL_COL32 = 2e-3
+TOL_ADJ = {"f64": 1e-12, "f32": 1e-5}
+TOL_COL32 = 5e-4
 
 
 def close(a, b, width, prec, tol):
@@ -84,6 +87,50 @@ def test_matches_oracle(name, compat, prec):
         assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
     if "gradient" in a:
         assert close(a["gradient"], b["gradient"], a["gradient"].size // E, prec, TOL_ADJ)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_call_order_matches_reference(prec):
+    """Repeated solver calls on ONE driver, pinned by a fixture of the unmodified reference
+    (tests/golden/ref_calls_ex1dof_short_*.npz): a second _getGradient without setJacobian continues from the adjoint state
+    and the forward state the first one left behind (g2 != g1), getAmplitudes after a gradient starts from that forward
+    state (a1 != a0) and resets it afterwards (a2 == a0)."""
+    z = golden("calls_ex1dof_short", prec)
+    case = wl.golden_case("calls_ex1dof_short")
+    p = frontend.make_frontend(capi.engine_class(prec))([np.array(r) for r in case["excitations"]], case["sample_rate"], case["numsteps"])
+    p.setSystems(*wl.to_frontend_args(case["systems"], frontend_mod))
+    out = wl.run_call_sequence(p, case, frontend_mod)
+    assert not np.array_equal(z["g1"], z["g2"]) and not np.array_equal(z["a0"], z["a1"]) and np.array_equal(z["a0"], z["a2"])
+    for k in ("a0", "a1", "a2"):
+        assert close(out[k], z[k], 4, prec, TOL_FWD), k
+    for k in ("g1", "g2"):
+        assert close(out[k], z[k], 6, prec, TOL_ADJ), k
+    assert np.array_equal(out["a0"], out["a2"])
+    # option call_order=independent: every call starts from the initial conditions
+    q = frontend.make_frontend(capi.engine_class(prec))([np.array(r) for r in case["excitations"]], case["sample_rate"], case["numsteps"])
+    q._setOption("call_order", "independent")
+    q.setSystems(*wl.to_frontend_args(case["systems"], frontend_mod))
+    ind = wl.run_call_sequence(q, case, frontend_mod)
+    assert np.array_equal(ind["g1"], ind["g2"]) and np.array_equal(ind["a0"], ind["a1"]) and np.array_equal(ind["g1"], out["g1"])
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_call_order_reseeding_matches_oracle(prec):
+    """The shipped example's re-seeding loop (examples/FullInterfaceTesting_1dof.py:233-237: _getGradient(save), then
+    setJacobian with the returned state as the adjoint initial condition).  The unmodified reference dies in this sequence
+    on a B200 (illegal memory access after the second setJacobian: its once-captured backward graph keeps pointers to the
+    freed adjoint buffers, quirk A9), so the pin is the literal restatement, whose call-order state matches the
+    reference's fixture in test_oracle.py."""
+    case = wl.golden_case("calls_ex1dof_e1")
+    outs = []
+    for drv in (capi.engine_class(prec), _oracle_driver(prec)):
+        p = frontend.make_frontend(drv)([np.array(r) for r in case["excitations"]], case["sample_rate"], case["numsteps"])
+        p.setSystems(*wl.to_frontend_args(case["systems"], frontend_mod))
+        outs.append(wl.run_call_sequence(p, case, frontend_mod))
+    a, b = outs
+    assert set(a) == set(b) and "s2" in a
+    for k in a:
+        assert close(a[k], b[k], 4 if k[0] == "a" else 6, prec, TOL_FWD if k[0] == "a" else TOL_ADJ), k
 
 
 def test_save_argument_stops_after_chunk():
@@ -170,11 +217,13 @@ def test_full_size_properties_many_systems():
     p = P([np.array(r) for r in exc], 16000, 0)
     p.setSystems(*wl.to_frontend_args([base[i] for i in pick], frontend_mod))
     p.setJacobian(*wl.to_frontend_args([jbase[i] for i in pick], frontend_mod, with_psi=True))
+    p._setOption("call_order", "independent")      # every call starts from the initial conditions (reference: quirk A7)
     amp = np.asarray(p.getAmplitudes()).reshape(64, S, 8)
     grad = np.asarray(p.getGradient()).reshape(64, S, 12)
     assert np.array_equal(np.asarray(p.getGradient()).reshape(64, S, 12), grad)
     for k in range(3):
         q = P([np.array(r) for r in exc], 16000, 0)
+        q._setOption("call_order", "independent")
         q.setSystems(*wl.to_frontend_args([base[k]], frontend_mod))
         q.setJacobian(*wl.to_frontend_args([jbase[k]], frontend_mod, with_psi=True))
         a1 = np.asarray(q.getAmplitudes()).reshape(64, 8)
