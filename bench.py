@@ -521,7 +521,7 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
                                        "frac": pairs * L * sz / (fwd_ms / steps * 1e-3) / 1e9 / ctx.peaks.get("hbm_gbs", 6650.0),
                                        "note": "one excitation sample per trajectory-step"}})
         if do_e2e:
-            entry["e2e"] = {"value": tot_pairs * L * e2e_steps / e2e_t, "unit": "system-steps/s", "h2d_bytes_per_step": int(job.exc.nbytes),
+            entry["e2e"] = {"value": tot_pairs * L * e2e_steps / e2e_t, "unit": "system-steps/s", "h2d_bytes_per_step": int(p._query("last_h2d_bytes")),
                             "d2h_bytes_per_step": int(d2h_bytes), "ms_per_step": e2e_t / e2e_steps * 1e3, "parts": e2e_parts}
         p.close()
         return entry
@@ -640,9 +640,10 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
         "wall_s_grad_steps": wall_grad,
     })
     if do_e2e:
-        entry["e2e"] = {"value": tot_pairs * e2e_steps / e2e_t, "unit": "gradient evals/s", "h2d_bytes_per_step": int(job.exc.nbytes),
+        entry["e2e"] = {"value": tot_pairs * e2e_steps / e2e_t, "unit": "gradient evals/s", "h2d_bytes_per_step": int(p._query("last_h2d_bytes")),
                         "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,
-                        "host_buffers": "pageable numpy arrays through the C ABI, staged through two pinned slots inside the engine",
+                        "host_buffers": "pageable float64 numpy arrays through the C ABI, staged through two pinned slots inside the engine "
+                                        "(an fp32 engine narrows the samples to float while staging: half the bytes cross the link)",
                         "ms_per_step": e2e_t / e2e_steps * 1e3, "parts": e2e_parts}
     if multi:
         ar_min, ar_max = min(per_rank_ar), max(per_rank_ar)

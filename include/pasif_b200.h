@@ -62,6 +62,10 @@ int pasif_alloc_adjoint(pasif_engine* e);
 
 /* _setInterpolationMatrix (src/__GpuDriver.cu:383-398): table = 2 x window row-major, window a power of two */
 int pasif_set_interp(pasif_engine* e, const double* table, uint32_t table_len, uint32_t window);
+/* additive: the 2 x W table of LINEAR interpolation between consecutive samples, generated on the device (what a caller of
+ * the reference builds on the host and passes to _setInterpolationMatrix; layout read by interpolateForces_fwd,
+ * src/kernels.cu:114-124: IM[j] = j / W weighs exc[o + 1], IM[W + j] = 1 - j / W weighs exc[o]).  W must be a power of two. */
+int pasif_set_interp_linear(pasif_engine* e, uint32_t window);
 /* _setModulationBuffer (src/__GpuDriver.cu:400-410): accepted and stored; no reference kernel reads it */
 int pasif_set_modulation(pasif_engine* e, const double* buffer, uint32_t n);
 
@@ -104,7 +108,8 @@ int pasif_fma_peak(int device, int dtype, double* tflops);
 /* isolated check of the dense-operator path's GEMM kernels (no reference counterpart: replaces the cusparseSpMM of
  * src/__GpuDriver.cu:795-807 for a dense shared K'): y[p][m] = sum_k kd[m][k] * x[p][k], kd [n][n], x / y [n_traj][n], row-major doubles.
  * mode 0: mma.sync kernel of the dtype (fp64 DMMA, fp32 3xTF32); mode 1: tcgen05 3xTF32 with pre-split operands (fp32 only);
- * mode 2: tcgen05 3xTF32 that splits the fp32 operand in shared memory (fp32 only) */
+ * mode 2: tcgen05 3xTF32 that splits the fp32 operand in shared memory (fp32 only); mode 4: the same with 256-row tiles;
+ * modes 5 / 6: modes 2 / 4 with 16-float k-blocks (64-byte swizzle, twice the pipeline stages) */
 int pasif_debug_gemm(int device, int dtype, int mode, uint32_t n, uint64_t n_traj, const double* kd, const double* x, double* y);
 
 #ifdef __cplusplus

@@ -18,7 +18,7 @@ LIB_PATH = os.environ.get("PASIF_B200_LIB") or os.path.join(HERE, "libpasif_b200
 SYMBOLS = """pasif_create pasif_destroy pasif_last_error pasif_load_excitations
 pasif_set_fwd_k pasif_set_fwd_gamma pasif_set_fwd_lambda pasif_set_fwd_psi pasif_set_fwd_force pasif_set_fwd_ic pasif_alloc_system
 pasif_set_bwd_k pasif_set_bwd_gamma pasif_set_bwd_lambda pasif_set_bwd_psi pasif_set_bwd_force pasif_set_bwd_ic pasif_alloc_adjoint
-pasif_set_interp pasif_set_modulation pasif_set_option
+pasif_set_interp pasif_set_interp_linear pasif_set_modulation pasif_set_option
 pasif_get_amplitudes pasif_trajectory_size pasif_get_trajectory pasif_get_gradient pasif_get_gradient_reduced
 pasif_get_gradient_reduced_device pasif_reduce_last_gradient_device pasif_query pasif_emit_patterns pasif_fma_peak pasif_debug_gemm pasif_debug_jit_log""".split()
 
@@ -49,6 +49,7 @@ def lib():
         L.pasif_alloc_system.argtypes = [C.c_void_p]
         L.pasif_alloc_adjoint.argtypes = [C.c_void_p]
         L.pasif_set_interp.argtypes = [C.c_void_p, _dp, C.c_uint32, C.c_uint32]
+        L.pasif_set_interp_linear.argtypes = [C.c_void_p, C.c_uint32]
         L.pasif_set_option.argtypes = [C.c_void_p, C.c_char_p, C.c_char_p]
         L.pasif_get_amplitudes.argtypes = [C.c_void_p, _dp, C.c_uint64]
         L.pasif_trajectory_size.argtypes = [C.c_void_p, C.c_uint32]
@@ -162,6 +163,10 @@ class Engine:
     def _setInterpolationMatrix(self, interpolationMatrix_, interpolationWindowSize_):
         v, pv = _d(interpolationMatrix_)
         self._check(lib().pasif_set_interp(self._h, pv, v.size, int(interpolationWindowSize_)))
+
+    def _setInterpolationLinear(self, interpolationWindowSize_):
+        """additive: linear 2 x W interpolation table generated on the device"""
+        self._check(lib().pasif_set_interp_linear(self._h, int(interpolationWindowSize_)))
 
     def _setModulationBuffer(self, modulationBuffer_): self._set_v(lib().pasif_set_modulation, modulationBuffer_)
 

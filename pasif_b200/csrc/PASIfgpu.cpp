@@ -75,6 +75,7 @@ class GpuDriver {
     return 0;
   }
   void setInterpolationMatrix(darr m, uint window) { check(pasif_set_interp(h, m.data(), (uint32_t)m.size(), window)); }
+  void setInterpolationLinear(uint window) { check(pasif_set_interp_linear(h, window)); }
   void setModulationBuffer(darr m) { check(pasif_set_modulation(h, m.data(), (uint32_t)m.size())); }
   void setOption(const std::string& k, const std::string& v) { check(pasif_set_option(h, k.c_str(), v.c_str())); }
   double query(const std::string& k) {
@@ -174,6 +175,7 @@ PYBIND11_MODULE(PASIfgpu, m) {
       .def("_loadExcitationsSet", &GpuDriver::loadExcitationsSet, py::arg("excitationSet_"), py::arg("sampleRate_"))
       .def("_setInterpolationMatrix", &GpuDriver::setInterpolationMatrix, py::arg("interpolationMatrix_"),
            py::arg("interpolationWindowSize_"))
+      .def("_setInterpolationLinear", &GpuDriver::setInterpolationLinear, py::arg("interpolationWindowSize_"))
       .def("_setModulationBuffer", &GpuDriver::setModulationBuffer, py::arg("modulationBuffer_"))
       // solvers interface
       .def("_getAmplitudes", &GpuDriver::getAmplitudes)

@@ -113,13 +113,15 @@ namespace {
 
 // raw [E][L] double  ->  gated compute-type samples [rows][E]: row t holds exc[e][t] for 0 < t < L, else 0.
 // The gate reproduces applyForces' `0 < step < L` (reference src/kernels.cu:82-87): a gated-out sample adds F*0.
-template <typename T>
-__global__ void prep_exc_full_kernel(const double* __restrict__ raw, T* __restrict__ out, int E, int L, int rows) {
-  __shared__ double tile[32][33];
+// R: type of the staged samples -- double as handed over, or float when the host staged them in single precision (fp32
+// engines: bit-identical, the cast happens on the host instead of here; fp64 engines: option exc_storage=f32)
+template <typename T, typename R>
+__global__ void prep_exc_full_kernel(const R* __restrict__ raw, T* __restrict__ out, int E, int L, int rows) {
+  __shared__ R tile[32][33];
   const int t0 = blockIdx.x * 32, e0 = blockIdx.y * 32;
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
     const int e = e0 + j, t = t0 + threadIdx.x;
-    tile[j][threadIdx.x] = (e < E && t > 0 && t < L) ? raw[(long long)e * L + t] : 0.0;
+    tile[j][threadIdx.x] = (e < E && t > 0 && t < L) ? raw[(long long)e * L + t] : R(0);
   }
   __syncthreads();
   for (int j = threadIdx.y; j < 32; j += blockDim.y) {
@@ -131,8 +133,8 @@ __global__ void prep_exc_full_kernel(const double* __restrict__ raw, T* __restri
 // interpolated half-step force stream f[u][e], u = 2*step + half (reference interpolateForces_fwd,
 // src/kernels.cu:96-126): j = u & (W-1), o = u >> log2(W), 0 < o < L ? IM[W+j]*exc[o] + IM[j]*exc[o+1] : 0,
 // exc[o+1] taken from the reference's flat [e][t] buffer (next excitation's first sample at o = L-1; 0 past the end).
-template <typename T>
-__global__ void prep_exc_half_kernel(const double* __restrict__ raw, const T* __restrict__ table, T* __restrict__ out,
+template <typename T, typename R>
+__global__ void prep_exc_half_kernel(const R* __restrict__ raw, const T* __restrict__ table, T* __restrict__ out,
                                      int E, int L, long long U, int W, int log2W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= U * E) return;
@@ -149,6 +151,19 @@ __global__ void prep_exc_half_kernel(const double* __restrict__ raw, const T* __
     v = table[W + j] * x0 + table[j] * x1;
   }
   out[idx] = v;
+}
+
+// 2 x W table of linear interpolation between consecutive samples, generated on the device (the table a caller of the
+// reference would build on the host and pass to setInterpolationMatrix; interpolateForces_fwd reads IM[W + j] as the weight
+// of exc[o] and IM[j] as the weight of exc[o + 1], src/kernels.cu:114-124): IM[j] = j / W, IM[W + j] = 1 - j / W, evaluated
+// in double and rounded to the compute type exactly like a host-built float64 table handed through the boundary.
+template <typename T>
+__global__ void gen_linear_table_kernel(T* __restrict__ table, int W) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= W) return;
+  const double w = (double)j / (double)W;
+  table[j] = (T)w;
+  table[W + j] = (T)(1.0 - w);
 }
 
 // G = lanes per trajectory (1 for ordinary classes): thread-trajectory p -> lane p % G of trajectory p / G = inst * E + e,
@@ -463,6 +478,9 @@ struct pasif_engine {
   SystemData fwd, bwd;
   std::vector<double> interp_table, modulation;
   uint32_t interp_window = 0;
+  bool interp_linear = false;                      // the 2 x W table is the linear one, generated on the device
+  bool exc_storage_f32 = false;                    // fp64 engines: stage / keep the excitation samples in single precision
+  bool raw_f32 = false;                            // what d_raw currently holds
   std::vector<DevClass> fwd_classes, joint_classes;
   bool fwd_ready = false, joint_ready = false;
   bool exc_dirty = true;
@@ -482,7 +500,8 @@ struct pasif_engine {
   bool fwd_dirty = false;
   DevBuf d_fwd_cur, d_q0, d_qend;                  // [E][N_glob] | class-layout start state | class-layout end state
   int d_user_kind = 0;                             // what d_user holds: 0 nothing | 1 amplitudes [E][N] | 2 adjoint state [E][N_adj]
-  double last_h2d_ms = 0, last_d2h_ms = 0;         // host wall time of the last staged upload / download
+  double last_h2d_ms = 0, last_d2h_ms = 0;
+  size_t last_h2d_bytes = 0;                       // bytes the last excitation upload moved over the host link         // host wall time of the last staged upload / download
   long long exc_rows = 0;
   bool exc_half = false;
   cudaStream_t stream = nullptr, stream2 = nullptr;   // stream2: adjoint sweep of chunk k overlaps the recompute of chunk k-1
@@ -516,6 +535,7 @@ struct pasif_engine {
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
   bool tc_multicast = false;                     // fused-split GEMM on clusters of two CTAs with the K' tile multicast (experimental)
   bool stage_direct = true;                      // dense-operator path: the state array is the stage vector of stage 1 (stage 4 writes one array)
+  int tc_bk = 16;                                // fused-split GEMM: floats per k-block (16: 64-byte swizzle, twice the pipeline stages; 32: r01)
   int tc_bn = 256;                               // fused-split GEMM: 256-row tiles when the band of dense rows is a multiple of 256 (else 128 / 192)
   bool tc_fused_split = true;                    // tcgen05 GEMM splits the fp32 stage vector into tf32 hi / lo in shared memory
   bool gemm_band = true;                         // dense-operator path: only the band of dense rows goes through the GEMM
@@ -832,21 +852,27 @@ void ensure_excitations(pasif_engine& E) {
     const long long rows = (long long)std::max(E.L, E.numsteps) + 8;
     E.d_exc.reserve((size_t)rows * E.E * sizeof(T));
     dim3 grid((unsigned)((rows + 31) / 32), (unsigned)((E.E + 31) / 32)), blk(32, 8);
-    prep_exc_full_kernel<T><<<grid, blk, 0, E.stream>>>((const double*)raw.p, (T*)E.d_exc.p, (int)E.E, (int)E.L, (int)rows);
+    if (E.raw_f32) prep_exc_full_kernel<T, float><<<grid, blk, 0, E.stream>>>((const float*)raw.p, (T*)E.d_exc.p, (int)E.E, (int)E.L, (int)rows);
+    else prep_exc_full_kernel<T, double><<<grid, blk, 0, E.stream>>>((const double*)raw.p, (T*)E.d_exc.p, (int)E.E, (int)E.L, (int)rows);
     E.exc_rows = rows;
   } else {
     const uint32_t W = E.interp_window;
-    if (E.interp_table.size() < 2ull * W)
+    if (!E.interp_linear && E.interp_table.size() < 2ull * W)
       throw std::runtime_error("interpolation table must hold 2 x window entries (the reference kernel reads IM[W + j], "
                                "src/kernels.cu:124)");
     const int log2W = (int)(unsigned)std::log2f((float)W);
     const long long U = 2ll * E.numsteps + 8;
     DevBuf tab;
-    upload<T>(tab, E.interp_table);
+    if (E.interp_linear) {
+      tab.reserve(2ull * W * sizeof(T));
+      gen_linear_table_kernel<T><<<(W + 127) / 128, 128, 0, E.stream>>>((T*)tab.p, (int)W);
+    } else upload<T>(tab, E.interp_table);
     E.d_exc.reserve((size_t)U * E.E * sizeof(T));
     const long long n = U * E.E;
-    prep_exc_half_kernel<T><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>((const double*)raw.p, (const T*)tab.p,
-                                                                                (T*)E.d_exc.p, (int)E.E, (int)E.L, U, (int)W, log2W);
+    if (E.raw_f32) prep_exc_half_kernel<T, float><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(
+        (const float*)raw.p, (const T*)tab.p, (T*)E.d_exc.p, (int)E.E, (int)E.L, U, (int)W, log2W);
+    else prep_exc_half_kernel<T, double><<<(unsigned)((n + 255) / 256), 256, 0, E.stream>>>(
+        (const double*)raw.p, (const T*)tab.p, (T*)E.d_exc.p, (int)E.E, (int)E.L, U, (int)W, log2W);
     CUDA_CHECK(cudaStreamSynchronize(E.stream));
     tab.release();
     E.exc_rows = U;
@@ -928,6 +954,27 @@ void h2d_staged(pasif_engine& E, void* dst, const void* src, size_t bytes) {
     const char* sp = (const char*)src + off;
     host_parallel(len, (size_t)1 << 20, [&](size_t b, size_t e) { std::memcpy(h + b, sp + b, e - b); });
     CUDA_CHECK(cudaMemcpyAsync((char*)dst + off, h, len, cudaMemcpyHostToDevice, E.stream));
+    CUDA_CHECK(cudaEventRecord(E.ev_stage[slot], E.stream));
+  }
+  E.last_h2d_ms = wall_ms() - t0;
+}
+
+// the same with the samples narrowed to float on the host while they are copied into the pinned slot: half the bytes cross
+// the host link.  An fp32 engine rounds every sample to float anyway ((T)raw in the prep kernels), so for it this is
+// bit-identical; an fp64 engine does it only on request (option exc_storage=f32).
+void h2d_staged_f32(pasif_engine& E, float* dst, const double* src, size_t n) {
+  const double t0 = wall_ms();
+  E.h_stage.reserve(2 * kStageSlot);
+  const size_t per = kStageSlot / sizeof(float);
+  size_t i = 0;
+  for (size_t off = 0; off < n; off += per, ++i) {
+    const size_t len = std::min(per, n - off);
+    const int slot = (int)(i & 1);
+    float* h = (float*)((char*)E.h_stage.p + slot * kStageSlot);
+    CUDA_CHECK(cudaEventSynchronize(E.ev_stage[slot]));
+    const double* sp = src + off;
+    host_parallel(len, (size_t)1 << 18, [&](size_t b, size_t e) { for (size_t k = b; k < e; ++k) h[k] = (float)sp[k]; });
+    CUDA_CHECK(cudaMemcpyAsync(dst + off, h, len * sizeof(float), cudaMemcpyHostToDevice, E.stream));
     CUDA_CHECK(cudaEventRecord(E.ev_stage[slot], E.stream));
   }
   E.last_h2d_ms = wall_ms() - t0;
@@ -1301,9 +1348,12 @@ void load_exc(pasif_engine& E, const double* exc, uint32_t n_exc, uint32_t lengt
     // straight to the device, as the reference does (src/__GpuDriver.cu:343-381), but through pinned staging and
     // without a host-side copy; the layout/precision pass runs on the device before the next solve
     CUDA_CHECK(cudaSetDevice(E.device));
-    const size_t bytes = (size_t)n_exc * length * sizeof(double);
-    E.d_raw.reserve(bytes);
-    h2d_staged(E, E.d_raw.p, exc, bytes);
+    const size_t n = (size_t)n_exc * length;
+    E.raw_f32 = E.dtype == PASIF_F32 || E.exc_storage_f32;
+    E.last_h2d_bytes = n * (E.raw_f32 ? sizeof(float) : sizeof(double));
+    E.d_raw.reserve(E.last_h2d_bytes);
+    if (E.raw_f32) h2d_staged_f32(E, (float*)E.d_raw.p, exc, n);
+    else h2d_staged(E, E.d_raw.p, exc, n * sizeof(double));
   }
   E.have_exc = true;
   E.exc_dirty = true;
@@ -1457,12 +1507,24 @@ int pasif_alloc_adjoint(pasif_engine* e) {
 
 int pasif_set_interp(pasif_engine* e, const double* table, uint32_t table_len, uint32_t window) {
   PASIF_TRY(e)
+  e->interp_linear = false;
   if (window == 0) { e->interp_table.clear(); e->interp_window = 0; }
   else {
     if (!table || table_len == 0) throw std::runtime_error("empty interpolation table");
     e->interp_table.assign(table, table + table_len);
     e->interp_window = window;
   }
+  e->exc_dirty = true;
+  PASIF_CATCH(e)
+}
+int pasif_set_interp_linear(pasif_engine* e, uint32_t window) {
+  PASIF_TRY(e)
+  if (window == 0 || (window & (window - 1)) != 0)
+    throw std::runtime_error("the interpolation window must be a power of two (the reference indexes the table with u & (W - 1), "
+                             "src/kernels.cu:114)");
+  e->interp_table.clear();
+  e->interp_window = window;
+  e->interp_linear = true;
   e->exc_dirty = true;
   PASIF_CATCH(e)
 }
@@ -1512,6 +1574,10 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     else CUDA_CHECK(cudaStreamCreateWithFlags(&e->stream2, cudaStreamNonBlocking));
   } else if (k == "stage_direct") {
     e->stage_direct = (v == "on" || v == "1");
+  } else if (k == "tc_bk") {
+    const int b = std::atoi(v.c_str());
+    if (b != 16 && b != 32) throw std::runtime_error("tc_bk must be 16 or 32");
+    e->tc_bk = b;
   } else if (k == "tc_bn") {
     e->tc_bn = std::atoi(v.c_str());
   } else if (k == "tc_multicast") {
@@ -1558,6 +1624,13 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->overlap = (v == "on" || v == "1");
   } else if (k == "profile") {
     e->profile = (v == "on" || v == "1");
+  } else if (k == "exc_storage") {
+    // fp64 engines: "f32" narrows the excitation samples to float on the host before they cross the link and keeps them
+    // so on the device (half the upload and half the footprint of the staged set; every sample carries a relative
+    // rounding error <= 6e-8, measured effect on the C2 gradient in tests/test_excitations_gpu.py); "f64": as handed over.
+    // fp32 engines always stage in float (bit-identical).  Takes effect at the next pasif_load_excitations.
+    if (v != "f32" && v != "f64") throw std::runtime_error("exc_storage must be 'f32' or 'f64'");
+    e->exc_storage_f32 = (v == "f32");
   } else if (k == "trim") {
     // gives back device memory held between calls: the kept chunk trajectories and the work arrays of the solvers
     if (!e->host_only) {
@@ -1638,6 +1711,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "stored_chunks") *value = (double)e->last_stored_chunks;
   else if (k == "chunks") *value = (double)e->last_chunks;
   else if (k == "last_h2d_ms") *value = e->last_h2d_ms;
+  else if (k == "last_h2d_bytes") *value = (double)e->last_h2d_bytes;
   else if (k == "last_d2h_ms") *value = e->last_d2h_ms;
   else if (k == "jit_compiles") *value = (double)e->jit_compiles;
   else if (k == "jit_cache_hits") *value = (double)e->jit_cache_hits;

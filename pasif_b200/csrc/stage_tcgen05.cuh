@@ -24,11 +24,16 @@ constexpr int TC_BK = 32;           // floats per k-block (128 bytes)
 constexpr int TC_A_BYTES = TC_BM * TC_BK * 4;          // 16 KB (one of hi / lo)
 // BN = rows of K' per tile (UMMA N): 192 for a full operator (544 rows = 3 tiles), 128 when only a band of dense rows goes
 // through the GEMM (256 rows = 2 tiles, no padding work); the narrower tile leaves room for a third pipeline stage
-template <int BN>
+// BK = floats per k-block: 32 (one 128-byte swizzle atom per row) or 16 (64-byte atoms).  With 256-row tiles a 32-float
+// stage is 96 KB -- two stages, and the tensor pipe then waits for TMA + hi/lo split of the NEXT stage (ncu r01: tensor pipe
+// 48 % active, 2.1 us per k-block against 1.1 us of MMA work); 16-float stages are 48 KB -- four stages, so the load of
+// k-block kb+2 and the split of kb+1 run under the MMAs of kb.
+template <int BN, int BK = TC_BK>
 struct TcCfg {
-  static constexpr int STAGES = BN <= 128 ? PASIF_TC_STAGES_128 : 2;
-  static constexpr int B_BYTES = BN * TC_BK * 4;        // 24 KB / 16 KB
-  static constexpr int STAGE_BYTES = 2 * TC_A_BYTES + 2 * B_BYTES;
+  static constexpr int A_BYTES = TC_BM * BK * 4;        // one of hi / lo
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = 2 * A_BYTES + 2 * B_BYTES;
+  static constexpr int STAGES = BK == 16 ? (BN <= 128 ? 6 : 4) : (BN <= 128 ? PASIF_TC_STAGES_128 : 2);
   static constexpr int SMEM = STAGES * STAGE_BYTES + 1024 /* alignment slack */ + 256 /* barriers */;
   static constexpr int TMEM_COLS = BN <= 128 ? 128 : 256;   // power of two >= BN
 };
@@ -61,6 +66,14 @@ __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, u
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   // K-major, SWIZZLE_128B: rows of 128 bytes, 8-row swizzle atoms 1024 bytes apart (SBO), LBO unused (1)
   return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);
+}
+__device__ __forceinline__ uint64_t umma_desc_sw64(uint32_t saddr) {
+  // K-major, SWIZZLE_64B: rows of 64 bytes, 8-row swizzle atoms 512 bytes apart (SBO); layout type 4
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)4 << 61);
+}
+template <int BK>
+__device__ __forceinline__ uint64_t umma_desc_k(uint32_t saddr) {
+  return BK == 16 ? umma_desc_sw64(saddr) : umma_desc_sw128(saddr);
 }
 __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
@@ -199,13 +212,14 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-template <int TC_BN>
+template <int TC_BN, int BK = TC_BK>
 __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                                const __grid_constant__ CUtensorMap mapBh,
                                                                                const __grid_constant__ CUtensorMap mapBl, float* __restrict__ Y,
                                                                                int M, int K, int ldy, int p_row0, int m_base, int k_base) {
-  constexpr int TC_STAGES = TcCfg<TC_BN>::STAGES, TC_B_BYTES = TcCfg<TC_BN>::B_BYTES, TC_STAGE_BYTES = TcCfg<TC_BN>::STAGE_BYTES,
-                TC_TMEM_COLS = TcCfg<TC_BN>::TMEM_COLS;
+  typedef TcCfg<TC_BN, BK> Cfg;
+  constexpr int TC_STAGES = Cfg::STAGES, TC_B_BYTES = Cfg::B_BYTES, TC_STAGE_BYTES = Cfg::STAGE_BYTES, TC_TMEM_COLS = Cfg::TMEM_COLS,
+                TC_A_BYTES = Cfg::A_BYTES;
   extern __shared__ unsigned char tc_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)tc_smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full = reinterpret_cast<uint64_t*>(base + TC_STAGES * TC_STAGE_BYTES);
@@ -216,7 +230,7 @@ __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(c
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int m0 = m_base + blockIdx.x * TC_BN;
   const int p0 = blockIdx.y * TC_BM;
-  const int nkb = K / TC_BK;
+  const int nkb = K / BK;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < TC_STAGES; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); mbar_init(&conv[s], 128); }
@@ -244,9 +258,9 @@ __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(c
         mbar_wait(&empty[s], ph ^ 1);
         unsigned char* st = base + s * TC_STAGE_BYTES;
         mbar_expect_tx(&full[s], TC_A_BYTES + 2 * TC_B_BYTES);
-        tma_load_2d(st, &mapA, &full[s], k_base + kb * TC_BK, p_row0 + p0);
-        tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], k_base + kb * TC_BK, m0);
-        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], k_base + kb * TC_BK, m0);
+        tma_load_2d(st, &mapA, &full[s], k_base + kb * BK, p_row0 + p0);
+        tma_load_2d(st + 2 * TC_A_BYTES, &mapBh, &full[s], k_base + kb * BK, m0);
+        tma_load_2d(st + 2 * TC_A_BYTES + TC_B_BYTES, &mapBl, &full[s], k_base + kb * BK, m0);
       }
     }
   } else if (warp == 5) {
@@ -261,11 +275,11 @@ __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(c
         const uint32_t sa = smem_u32(base + s * TC_STAGE_BYTES);
         const uint32_t a_hi = sa, a_lo = sa + TC_A_BYTES, b_hi = sa + 2 * TC_A_BYTES, b_lo = b_hi + TC_B_BYTES;
 #pragma unroll
-        for (int kk = 0; kk < TC_BK / 8; ++kk) {
+        for (int kk = 0; kk < BK / 8; ++kk) {
           const uint32_t o = kk * 32;
-          umma_tf32(tmem_d, umma_desc_sw128(a_lo + o), umma_desc_sw128(b_hi + o), idesc, (kb | kk) != 0);
-          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_lo + o), idesc, 1u);
-          umma_tf32(tmem_d, umma_desc_sw128(a_hi + o), umma_desc_sw128(b_hi + o), idesc, 1u);
+          umma_tf32(tmem_d, umma_desc_k<BK>(a_lo + o), umma_desc_k<BK>(b_hi + o), idesc, (kb | kk) != 0);
+          umma_tf32(tmem_d, umma_desc_k<BK>(a_hi + o), umma_desc_k<BK>(b_lo + o), idesc, 1u);
+          umma_tf32(tmem_d, umma_desc_k<BK>(a_hi + o), umma_desc_k<BK>(b_hi + o), idesc, 1u);
         }
         umma_commit(&empty[s]);
       }

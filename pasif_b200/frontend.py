@@ -238,6 +238,15 @@ def make_frontend(driver_cls):
             self.interpolationMatrix = np.array(interpolationMatrix_).flatten()
             self._setInterpolationMatrix(self.interpolationMatrix, len(interpolationMatrix_[0]))
 
+        def setLinearInterpolation(self, windowSize):
+            """Additive: up-sample the excitations by `windowSize` / 2 RK4 steps per sample with the LINEAR 2 x W table,
+            generated on the device -- the same result as ``setInterpolationMatrix`` with the table
+            ``[[j / W], [1 - j / W]]`` (what the reference's callers build on the host, PASIf.py:371-385)."""
+            if windowSize <= 0 or windowSize & (windowSize - 1):
+                raise ValueError("The windows size must be a power of two.")
+            self.interpolSize = 2
+            self._setInterpolationLinear(windowSize)
+
         def setModulationBuffer(self, modulationBuffer_):
             if len(modulationBuffer_) == 0:
                 raise ValueError("The modulation buffer must be non-empty.")

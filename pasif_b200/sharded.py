@@ -65,7 +65,9 @@ class ShardedPASIf:
         self._cls = make_frontend(driver_cls)
         self.axis = axis
         self.presharded = bool(presharded)
-        self.options = dict(options or {})
+        # every call of this (additive) front end starts from the initial conditions; the reference driver carries forward /
+        # adjoint state from one _getGradient into the next, which the engine reproduces by default
+        self.options = dict({"call_order": "independent"}, **(options or {}))
         self.local = None
         self.n_systems = 0
         self._sys_range = (0, 0)
@@ -110,8 +112,9 @@ class ShardedPASIf:
             raise ValueError("rank %d received an empty shard (%d systems, %d excitations over %d ranks)"
                              % (self.rank, self.n_systems, len(self._exc_all), self.world))
         self.local = self._cls(self._exc_all[e0:e1], sr, n, dc, ds, dv)
-        for k, v in self.options.items():
-            self.local._setOption(k, v)
+        if hasattr(self.local, "_setOption"):
+            for k, v in self.options.items():
+                self.local._setOption(k, v)
         self.local.setSystems(vecM[sl], vecB[sl], vecK[sl], vecGamma[sl], vecLambda[sl], vecForcePattern[sl],
                               vecInitialConditions[sl])
 
