@@ -226,11 +226,23 @@ def reference_gpu_sample(w):
                             "--systems", str(S), "--excitations", str(E), "--steps", str(steps), "--exc-seed", str(w["exc_seed"])],
                            capture_output=True, text=True, timeout=600)
         d = json.loads(r.stdout.strip().splitlines()[-1])
-        return {"value": d["gradient_trajectory_steps_per_s"] / w["L"], "unit": "gradient evals/s",
-                "forward_system_steps_per_s": d["forward_system_steps_per_s"], "gradient_s": d["gradient_s"], "forward_s": d["forward_s"],
-                "sample": f"unmodified reference (sm_100 build of src/*.cu, {w['dtype']}) through its own PASIf.py on this GPU: {S} systems x {E} "
-                          f"excitations x {steps} steps (its front end cannot assemble more than 2 Jacobians; its per-step cost is "
-                          f"launch-bound, i.e. independent of the batch at this size); evals/s scaled to {w['L']} steps"}
+        out = {"value": d["gradient_trajectory_steps_per_s"] / w["L"], "unit": "gradient evals/s",
+               "forward_system_steps_per_s": d["forward_system_steps_per_s"], "gradient_s": d["gradient_s"], "forward_s": d["forward_s"],
+               "sample": f"unmodified reference (sm_100 build of src/*.cu, {w['dtype']}) through its own PASIf.py on this GPU: {S} systems x {E} "
+                         f"excitations x {steps} steps (its front end cannot assemble more than 2 Jacobians; its per-step cost is "
+                         f"launch-bound, i.e. independent of the batch at this size); evals/s scaled to {w['L']} steps"}
+        # the headline batch itself, forward only (the one thing the reference can be timed on at this size: no Jacobians; its
+        # results are invalid there -- more than 128 nonlinear non-zeros, quirk F4 -- its time is still its time)
+        if w["n_systems"] > 2:
+            fsteps = 4000
+            r = subprocess.run([sys.executable, os.path.join(ROOT, "oracle", "time_reference_gpu.py"), "--prec", w["dtype"],
+                                "--systems", str(w["n_systems"]), "--excitations", str(E), "--steps", str(fsteps), "--exc-seed", str(w["exc_seed"]),
+                                "--forward-only"], capture_output=True, text=True, timeout=900)
+            f = json.loads(r.stdout.strip().splitlines()[-1])
+            out["forward_full_batch"] = {"system_steps_per_s": f["forward_system_steps_per_s"], "forward_s": f["forward_s"],
+                                         "setSystems_s": f["setSystems_s"], "results_valid": f["results_valid"],
+                                         "sample": f"{w['n_systems']} systems x {E} excitations x {fsteps} steps, getAmplitudes"}
+        return out
     except Exception as e:  # noqa
         return {"unavailable": repr(e)[:200]}
 
@@ -505,12 +517,23 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
     fwd_tf = pairs * L * job.F_FWD / (fwd_ms / steps * 1e-3) / 1e12
     entry["forward"] = {"metric": "RK4 system-steps/s", "value": fwd_value, "unit": "system-steps/s", "ms_per_step": fwd_ms / steps,
                         "roofline": {"bound": "fma", "achieved": fwd_tf, "peak": peak, "unit": "TFLOP/s", "frac": fwd_tf / peak}}
+    # a batch smaller than the machine: every warp of 32 trajectories (16 packed pairs x 2 in fp32) sits alone on one SM
+    # sub-partition and is bound by that partition's own FMA pipe; the chip-level fraction then mostly counts idle partitions
+    lanes_per_warp = 64 if (w["dtype"] == "f32" and E % 2 == 0 and not large) else 32
+    warps = -(-pairs // lanes_per_warp)
+    small_batch = None
+    if warps < 4 * ctx.n_sm and not large:
+        small_batch = {"warps": int(warps), "sm_subpartitions": 4 * ctx.n_sm,
+                       "note": "fewer warps than SM sub-partitions: fractions below are of the pipes of the sub-partitions the batch can occupy"}
     cfg = {"workload": w["name"], "systems_per_gpu": job.S_local, "systems_total": job.S_total, "excitations": E, "rk4_steps": L,
            "compat": a.compat, "sharding": ("system axis, fixed total (strong)" if strong else "system axis, per-GPU block (weak)") if multi else "single GPU",
            "l2": "working set (checkpoints + chunk trajectory) exceeds the 126 MB L2 for every throughput configuration; no flush needed",
            "timing": "CUDA events on the engine stream (+ events around the NCCL all-reduce), summed over the timed steps, max over ranks",
            "setup_s": job.setup_s, "two_trajectories_per_thread_ffma2": bool(p._query("pair_launches") > 0)}
     entry["config"] = cfg
+    if small_batch:
+        small_batch["forward_frac_of_occupied_subpartitions"] = entry["forward"]["roofline"]["frac"] * small_batch["sm_subpartitions"] / warps
+        entry["small_batch"] = small_batch
     entry["clocks"] = clocks
     entry["gpu_launches"] = launches
     if job.forward_only:
@@ -645,6 +668,8 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
                         "host_buffers": "pageable float64 numpy arrays through the C ABI, staged through two pinned slots inside the engine "
                                         "(an fp32 engine narrows the samples to float while staging: half the bytes cross the link)",
                         "ms_per_step": e2e_t / e2e_steps * 1e3, "parts": e2e_parts}
+    if small_batch:
+        small_batch["whole_step_frac_of_occupied_subpartitions"] = entry["roofline"]["whole_step"]["frac"] * small_batch["sm_subpartitions"] / warps
     if multi:
         ar_min, ar_max = min(per_rank_ar), max(per_rank_ar)
         d_min, d_max = min(per_rank_dev), max(per_rank_dev)

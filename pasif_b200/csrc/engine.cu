@@ -358,38 +358,30 @@ struct DriverApi {
 };
 DriverApi g_drv;
 
-std::string this_library_dir() {
-  Dl_info info;
-  if (dladdr((const void*)&pasif_create, &info) && info.dli_fname) {
-    std::string p(info.dli_fname);
-    size_t s = p.find_last_of('/');
-    return s == std::string::npos ? "." : p.substr(0, s);
-  }
-  return ".";
-}
-
 std::string read_file(const std::string& path) {
   std::ifstream f(path, std::ios::binary);
   if (!f) return std::string();
   return std::string((std::istreambuf_iterator<char>(f)), std::istreambuf_iterator<char>());
 }
 
+// text of rk4_kernels.cuh for run-time specialisation: compiled into the library (rk4_kernels_text.inc, written by
+// pasif_b200/build.py), so a deployed .so needs no source file beside it; PASIF_B200_KERNEL_HEADER overrides it (kernel
+// development without rebuilding the library)
+const char* const kEmbeddedKernelHeader =
+#include "rk4_kernels_text.inc"
+    ;
+
 std::string kernel_header_text() {
   static std::string cached;
   std::lock_guard<std::mutex> lk(g_init_mu);
   if (!cached.empty()) return cached;
-  std::vector<std::string> cand;
-  if (const char* env = getenv("PASIF_B200_KERNEL_HEADER")) cand.push_back(env);
-  const std::string d = this_library_dir();
-  cand.push_back(d + "/csrc/rk4_kernels.cuh");
-  cand.push_back(d + "/rk4_kernels.cuh");
-  cand.push_back(d + "/../pasif_b200/csrc/rk4_kernels.cuh");
-  for (auto& c : cand) {
-    cached = read_file(c);
-    if (!cached.empty()) return cached;
+  if (const char* env = getenv("PASIF_B200_KERNEL_HEADER")) {
+    cached = read_file(env);
+    if (cached.empty()) throw std::runtime_error(std::string("PASIF_B200_KERNEL_HEADER: cannot read ") + env);
+    return cached;
   }
-  throw std::runtime_error("rk4_kernels.cuh not found next to the library (needed for run-time specialisation); "
-                           "set PASIF_B200_KERNEL_HEADER");
+  cached = kEmbeddedKernelHeader;
+  return cached;
 }
 
 struct KernelHandle {

@@ -183,3 +183,12 @@ def test_emitted_traits_compile_standalone(tmp_path):
                        stderr=subprocess.STDOUT, text=True)
     assert r.returncode == 0, r.stdout
     assert "bytes spill" in r.stdout and not re.search(r"[1-9]\d* bytes spill", r.stdout), r.stdout
+
+
+def test_embedded_kernel_header_is_in_sync():
+    """rk4_kernels_text.inc (compiled into the library for NVRTC) is the current rk4_kernels.cuh."""
+    import os
+    from pasif_b200 import build as b
+    text = open(os.path.join(b.CSRC, "rk4_kernels.cuh")).read()
+    inc = open(os.path.join(b.CSRC, "rk4_kernels_text.inc")).read()
+    assert inc.split('R"PASIFHDR(', 1)[1].rsplit(')PASIFHDR"', 1)[0] == text
