@@ -424,11 +424,13 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
     wall0 = time.time()
     dev_ms = ar_ms = 0.0
     launches = 0
+    per_step = []                                    # (device ms, all-reduce ms) of every timed step on this rank
     if not job.forward_only:
         for _ in range(steps):
             d_ms, r_ms = grad_step_resident()
             dev_ms += d_ms
             ar_ms += r_ms
+            per_step += [d_ms, r_ms]
             launches += int(p._query("last_launches"))
     ctx.barrier()
     wall_grad = time.time() - wall0
@@ -492,13 +494,22 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
                 e2e_parts["h2d_staging_ms"] += p._query("last_h2d_ms") / e2e_steps
                 e2e_parts["d2h_staging_ms"] += p._query("last_d2h_ms") / e2e_steps
     # ---------------- max over ranks; per-rank device / all-reduce times
-    rows = ctx.gather([dev_ms + ar_ms, fwd_ms, e2e_t, wall_grad, dev_ms, ar_ms])
+    rows = ctx.gather([dev_ms + ar_ms, fwd_ms, e2e_t, wall_grad, dev_ms, ar_ms] + per_step)
     step_ms_tot = max(r[0] for r in rows)
     fwd_ms = max(r[1] for r in rows)
     e2e_t = max(r[2] for r in rows)
     wall_grad = max(r[3] for r in rows)
     per_rank_dev = [r[4] / max(steps, 1) for r in rows]
     per_rank_ar = [r[5] / max(steps, 1) for r in rows]
+    # per step: the rank that finishes its gradient last does not wait inside the collective, so min over ranks of that
+    # step's all-reduce time is the collective itself; max - min of the device times is that step's rank skew
+    nccl_ms = skew_ms = 0.0
+    if multi and not job.forward_only and steps:
+        for k in range(steps):
+            devs = [r[6 + 2 * k] for r in rows]
+            ars = [r[7 + 2 * k] for r in rows]
+            nccl_ms += min(ars) / steps
+            skew_ms += (max(devs) - min(devs)) / steps
     # ---------------- N > 1: the all-reduced vector against a single-GPU recompute of a slice (outside the timed region)
     check = None
     if multi and not job.forward_only:
@@ -673,13 +684,16 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
     if multi:
         ar_min, ar_max = min(per_rank_ar), max(per_rank_ar)
         d_min, d_max = min(per_rank_dev), max(per_rank_dev)
-        entry["allreduce_ms"] = {"min_over_ranks": ar_min, "max_over_ranks": ar_max, "bytes": int(job.red.numel() * sz),
-                                 "note": "CUDA events around dist.all_reduce on every rank; a rank that finishes its gradient early waits "
-                                         "inside the collective for the slowest rank, so the minimum over ranks is the collective itself and "
-                                         "(max - min) is rank skew"}
+        entry["allreduce_ms"] = {"collective": nccl_ms, "mean_min_over_ranks": ar_min, "mean_max_over_ranks": ar_max,
+                                 "bytes": int(job.red.numel() * sz),
+                                 "note": "CUDA events around dist.all_reduce on every rank and step; a rank that finishes its gradient early "
+                                         "waits inside the collective for the slowest rank, so `collective` = mean over steps of the minimum "
+                                         "over ranks is the all-reduce itself; the per-rank means include that waiting"}
         entry["device_ms_per_rank"] = {"min": d_min, "max": d_max, "all": per_rank_dev}
-        entry["scaling_loss"] = {"rank_skew_ms": d_max - d_min, "nccl_ms": ar_min,
-                                 "limiter": "rank skew (kernel time differs between GPUs)" if (d_max - d_min) > ar_min else "NCCL all-reduce"}
+        entry["scaling_loss"] = {"rank_skew_ms": skew_ms, "nccl_ms": nccl_ms,
+                                 "note": "per step: max - min over ranks of the local gradient's device time (skew) against the "
+                                         "collective's own time; means over the timed steps",
+                                 "limiter": "rank skew (kernel time differs between GPUs and steps)" if skew_ms > nccl_ms else "NCCL all-reduce"}
         entry["allreduce_check"] = check
     if lane:
         cfg["lane_split"] = {k: p._query("lane_" + k) for k in ("G", "R", "RA", "nv", "nc_fwd", "nc_adj", "halo_fwd", "halo_adj", "halo_p", "efficiency")}
