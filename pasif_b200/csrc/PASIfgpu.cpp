@@ -8,6 +8,9 @@
 //     extra keyword `dtype_` ("f64" | "f32") or environment PASIF_DTYPE, default f64;
 //   * the GIL is released while the device works;
 //   * engine options (adjoint schedule semantics etc.) through `_setOption(key, value)` or PASIF_COMPAT.
+// NOT a difference: repeated solver calls carry state like the reference driver's (a second _getGradient without setJacobian
+// continues from the previous forward / adjoint state, src/__GpuDriver.cu:522-523,743; getAmplitudes / getTrajectory reset the
+// forward state afterwards, :447,482) -- pinned by tests/golden/ref_calls_*.npz; `_setOption("call_order", "independent")` opts out.
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>

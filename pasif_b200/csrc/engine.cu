@@ -87,7 +87,7 @@ struct AotReg {
   __global__ void __launch_bounds__(PASIF_BLOCK) pasif_gfwd_f32_##TR(const pasif::FwdArgs<float> a) {           \
     pasif::forward_body<float, TR::Fwd, TR::Adj>(a);                                                            \
   }                                                                                                             \
-  __global__ void __launch_bounds__(PASIF_BLOCK) pasif_bwd_f64_##TR(const pasif::BwdArgs<double> a) {           \
+  __global__ void __launch_bounds__(PASIF_BLOCK, 4) pasif_bwd_f64_##TR(const pasif::BwdArgs<double> a) {        \
     pasif::backward_body<double, TR::Adj>(a);                                                                   \
   }                                                                                                             \
   __global__ void __launch_bounds__(PASIF_BLOCK) pasif_bwd_f32_##TR(const pasif::BwdArgs<float> a) {            \
@@ -599,7 +599,11 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
   } else {
     s += std::string("extern \"C\" __global__ void ") + lb(minb_fwd) + " pasif_k_gfwd(const pasif::FwdArgs<" + T +
          "> a) { pasif::forward_body<" + T + ", " + c.name + "::Fwd, " + c.name + "::Adj>(a); }\n";
-    s += std::string("extern \"C\" __global__ void ") + lb(minb_bwd) + " pasif_k_bwd(const pasif::BwdArgs<" + T +
+    // fp64 adjoint kernel of the 12-state example Jacobian: 162 registers uncapped = 3 CTAs per SM; capped at 128 (4 CTAs, no
+    // spills) it runs 5 % faster.  Same rule as for the fp32 pair kernel above; larger patterns keep the uncapped build.
+    const int est64 = 2 * (c.adj.nc() + 4 * c.adj.N + 4 * (int)c.adj.nv.size()) + 24;
+    const int cap_bwd = minb_bwd > 0 ? minb_bwd : ((dtype == PASIF_F64 && c.lanes == 1 && est64 <= 200) ? 4 : 0);
+    s += std::string("extern \"C\" __global__ void ") + lb(cap_bwd) + " pasif_k_bwd(const pasif::BwdArgs<" + T +
          "> a) { pasif::backward_body<" + T + ", " + c.name + "::Adj>(a); }\n";
   }
   return s;
