@@ -166,26 +166,35 @@ __global__ void gen_linear_table_kernel(T* __restrict__ table, int W) {
   table[W + j] = (T)(1.0 - w);
 }
 
-// G = lanes per trajectory (1 for ordinary classes): thread-trajectory p -> lane p % G of trajectory p / G = inst * E + e,
-// tables indexed by the virtual instance inst * G + lane (rk4_kernels.cuh, lane-block classes)
+// G = lanes per trajectory (1 for ordinary classes), W = trajectories per thread of the class's kernels (2: fp32 pair
+// kernels).  Slot p of a trajectory-minor array belongs to thread p / W: lane (p / W) % G of trajectory
+// ((p / W) / G) * W + p % W = inst * E + e; tables are indexed by the virtual instance inst * G + lane (rk4_kernels.cuh).
+// For G == 1 this is trajectory p whatever W is; for W == 1 the r01 mapping lane p % G, trajectory p / G.
+__device__ __forceinline__ void slot_to_lane_traj(int p, int G, int W, int& lane, int& traj) {
+  const int t = p / W;
+  lane = t % G;
+  traj = (t / G) * W + p % W;
+}
 template <typename T>
-__global__ void init_state_kernel(const T* __restrict__ ic, T* __restrict__ st, int N, int n_inst, int E, int n_traj, int G) {
+__global__ void init_state_kernel(const T* __restrict__ ic, T* __restrict__ st, int N, int n_inst, int E, int n_traj, int G, int W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * n_traj) return;
   const int i = (int)(idx / n_traj);
   const int p = (int)(idx - (long long)i * n_traj);
-  const int lane = p % G, traj = p / G;
+  int lane, traj;
+  slot_to_lane_traj(p, G, W, lane, traj);
   st[idx] = ic[(long long)i * n_inst + (traj / E) * G + lane];
 }
 
 template <typename T>
 __global__ void scatter_user_kernel(const T* __restrict__ st, const int* __restrict__ varmap, T* __restrict__ out,
-                                    int N, int n_inst, int E, int n_traj, int n_glob, int G) {
+                                    int N, int n_inst, int E, int n_traj, int n_glob, int G, int W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * n_traj) return;
   const int i = (int)(idx / n_traj);
   const int p = (int)(idx - (long long)i * n_traj);
-  const int lane = p % G, traj = p / G;
+  int lane, traj;
+  slot_to_lane_traj(p, G, W, lane, traj);
   const int e = traj % E, inst = (traj / E) * G + lane;
   const int g = varmap[(long long)i * n_inst + inst];
   if (g >= 0) out[(long long)e * n_glob + g] = st[idx];
@@ -195,12 +204,13 @@ __global__ void scatter_user_kernel(const T* __restrict__ st, const int* __restr
 // initial condition.  Used for the call-order state (a sweep that starts from the state a previous call left behind).
 template <typename T>
 __global__ void gather_user_kernel(const T* __restrict__ user, const int* __restrict__ varmap, const T* __restrict__ ic,
-                                   T* __restrict__ st, int N, int n_inst, int E, int n_traj, int n_glob, int G) {
+                                   T* __restrict__ st, int N, int n_inst, int E, int n_traj, int n_glob, int G, int W) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (long long)N * n_traj) return;
   const int i = (int)(idx / n_traj);
   const int p = (int)(idx - (long long)i * n_traj);
-  const int lane = p % G, traj = p / G;
+  int lane, traj;
+  slot_to_lane_traj(p, G, W, lane, traj);
   const int e = traj % E, inst = (traj / E) * G + lane;
   const int g = varmap[(long long)i * n_inst + inst];
   st[idx] = g >= 0 ? user[(long long)e * n_glob + g] : ic[(long long)i * n_inst + inst];
@@ -512,6 +522,7 @@ struct pasif_engine {
   int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
   bool unit_on = true;                           // register kernels: K terms with coefficient exactly 1 become additions
   bool pair_on = true;                           // fp32 one-thread classes: two trajectories per thread (packed FFMA2)
+  bool lane_pair_on = true;                      // lane-block classes of an fp32 engine: pair kernels, split sized for them
   int pair_regs = 230;                           // register estimate up to which the pair kernels are used
   long long pair_launches = 0;
   bool aot_on = true;                            // use the prebuilt kernels when a pattern matches (off: always specialise at run time)
@@ -578,7 +589,7 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
   const char* T = dtype == PASIF_F32 ? "float" : "double";
   // minb > 0: __launch_bounds__(PASIF_BLOCK, minb) -- caps the registers so that `minb` CTAs fit an SM (lane-block classes)
   auto lb = [](int minb) { return minb > 0 ? "__launch_bounds__(PASIF_BLOCK, " + std::to_string(minb) + ")" : std::string("__launch_bounds__(PASIF_BLOCK)"); };
-  const bool pair = dtype == PASIF_F32 && c.lanes == 1;
+  const bool pair = dtype == PASIF_F32 && (c.lanes == 1 || c.lane_pair);
   if (pair) {
     if (!c.joint)
       s += "extern \"C\" __global__ void " + lb(minb_fwd) + " pasif_k_fwd2(const pasif::FwdArgs<float> a) { pasif::forward_body<float, " +
@@ -589,7 +600,7 @@ std::string jit_source(const ClassData& c, int dtype, int minb_fwd = 0, int minb
       // the adjoint pair kernel of the 12-state example Jacobian needs 150 registers uncapped = 3 CTAs per SM; capped at 128
       // (4 CTAs) it runs 4 % faster (profiles/r02_probe_pair_variants.json).  Larger patterns keep the uncapped build.
       const int est = c.adj.nc() + 8 * c.adj.N + 8 * (int)c.adj.nv.size() + 24;
-      s += "extern \"C\" __global__ void " + lb(minb_bwd > 0 ? minb_bwd : (est <= 180 ? 4 : 0)) + " pasif_k_bwd2(const pasif::BwdArgs<float> a) { pasif::backward_body<float, " +
+      s += "extern \"C\" __global__ void " + lb(minb_bwd > 0 ? minb_bwd : ((c.lanes == 1 && est <= 180) ? 4 : 0)) + " pasif_k_bwd2(const pasif::BwdArgs<float> a) { pasif::backward_body<float, " +
            c.name + "::Adj, 2>(a); }\n";
     }
   }
@@ -697,7 +708,7 @@ void resolve_kernels(pasif_engine& E, DevClass& dc) {
   };
   if (!c.joint) getf("pasif_k_fwd", &dc.k_fwd.jit);
   else { getf("pasif_k_gfwd", &dc.k_gfwd.jit); getf("pasif_k_bwd", &dc.k_bwd.jit); }
-  if (E.dtype == PASIF_F32 && c.lanes == 1) {
+  if (E.dtype == PASIF_F32 && (c.lanes == 1 || c.lane_pair)) {
     if (!c.joint) getf("pasif_k_fwd2", &dc.k_fwd2.jit);
     else { getf("pasif_k_gfwd2", &dc.k_gfwd2.jit); getf("pasif_k_bwd2", &dc.k_bwd2.jit); }
   }
@@ -743,13 +754,15 @@ void launch(pasif_engine& E, const KernelHandle& k, long long n_threads, Args& a
 // rk4_kernels.cuh): the pair (e, e+1) belongs to one instance and every 8-byte access is aligned.  Bit-identical to the
 // one-trajectory kernels; option pair=off keeps those.
 bool use_pairs(const pasif_engine& E, const DevClass& c) {
+  if (!E.pair_on || E.dtype != PASIF_F32 || c.large || E.E % 2 != 0) return false;
+  if (!(c.h.joint ? c.k_gfwd2.valid() && c.k_bwd2.valid() : c.k_fwd2.valid())) return false;
+  // lane-block classes: only when the split was sized for pairs (lane_split.hpp: state slots counted twice)
+  if (c.h.lanes > 1) return c.h.lane_pair;
   // register estimate of the pair kernels (calibrated with ptxas -v: 8-state system 100, 12-state adjoint 152): coefficients
   // stay scalars, every state slot doubles; beyond the register file's comfortable range the one-trajectory kernels stay
   const long long est = std::max<long long>(c.h.fwd.nc() + 8ll * c.h.fwd.N,
                                             c.h.joint ? c.h.adj.nc() + 8ll * c.h.adj.N + 8ll * (long long)c.h.adj.nv.size() : 0) + 24;
-  if (est > E.pair_regs) return false;
-  return E.pair_on && E.dtype == PASIF_F32 && c.h.lanes == 1 && !c.large && E.E % 2 == 0 &&
-         (c.h.joint ? c.k_gfwd2.valid() && c.k_bwd2.valid() : c.k_fwd2.valid());
+  return est <= E.pair_regs;
 }
 
 void free_classes(std::vector<DevClass>& v) {
@@ -793,7 +806,10 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
       LaneSplitReport rep;
       bool ok = false;
       try {
-        ok = lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, E.lane_min_eff, split, rep);
+        // fp32 with an even number of excitations: the class will run two trajectories per thread (packed FFMA2), so the
+        // split is sized with every state slot counted twice (it then picks a group twice as wide)
+        const bool pair_mode = sizeof(T) == 4 && E.pair_on && E.lane_pair_on && E.E % 2 == 0;
+        ok = lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, E.lane_min_eff, split, rep, pair_mode);
       } catch (const std::exception& ex) {       // a split that fails its own check is never used: the other paths take over
         rep.why = ex.what();
         ++E.lane_selfcheck_failures;
@@ -1017,7 +1033,7 @@ const T* gather_start_state(pasif_engine& E, const DevClass& c) {
   E.d_q0.reserve((size_t)std::max<long long>(tot, 1) * sizeof(T));
   gather_user_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>(
       (const T*)E.d_fwd_cur.p, (const int*)c.varmap.p, (const T*)c.ic.p, (T*)E.d_q0.p, c.h.fwd.N, c.h.n_inst, (int)E.E,
-      (int)c.n_traj, (int)E.fwd.n, c.h.lanes);
+      (int)c.n_traj, (int)E.fwd.n, c.h.lanes, use_pairs(E, c) ? 2 : 1);
   ++E.last_launches;
   return (const T*)E.d_q0.p;
 }
@@ -1052,7 +1068,7 @@ void solve_forward(pasif_engine& E, uint32_t save_steps, double* out, uint64_t n
     } else {
       a.final_user = (T*)E.d_user.p;
     }
-    if (use_pairs(E, c)) { launch(E, c.k_fwd2, c.n_traj / 2, a, 0, nullptr, 1); ++E.pair_launches; }
+    if (use_pairs(E, c)) { launch(E, c.k_fwd2, c.n_traj / 2, a, 0, nullptr, c.h.lanes); ++E.pair_launches; }
     else launch(E, c.k_fwd, c.n_traj, a, 0, nullptr, c.h.lanes);
   }
   end_timing(E);
@@ -1103,7 +1119,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     } else {
       const long long tot = (long long)NA * P;
       init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-          (const T*)c.ic_adj.p, (T*)E.d_lam.p, NA, c.h.n_inst, (int)E.E, (int)P, c.h.lanes);
+          (const T*)c.ic_adj.p, (T*)E.d_lam.p, NA, c.h.n_inst, (int)E.E, (int)P, c.h.lanes, pairs ? 2 : 1);
       ++E.last_launches;
     }
     const T* q_start = (carry && E.fwd_dirty) ? gather_start_state<T>(E, c) : nullptr;
@@ -1168,7 +1184,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
           a.save_phase = 1;                        // slot j <- state BEFORE step j*c; slot 0 = initial condition
           const long long tot = (long long)NF * P;
           init_state_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-              (const T*)c.ic.p, ckpt, NF, c.h.n_inst, (int)E.E, (int)P, c.h.lanes);
+              (const T*)c.ic.p, ckpt, NF, c.h.n_inst, (int)E.E, (int)P, c.h.lanes, pairs ? 2 : 1);
           ++E.last_launches;
           const long long t_split = std::min<long long>(n, sp_store * chunk);
           if (t_split > 0) {                       // checkpoints only
@@ -1237,7 +1253,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
     }
     const long long tot = (long long)NA * P;
     scatter_user_kernel<T><<<(unsigned)((tot + threads - 1) / threads), threads, 0, E.stream>>>(
-        (const T*)E.d_lam.p, (const int*)c.varmap_adj.p, d_user_out, NA, c.h.n_inst, (int)E.E, (int)P, (int)E.bwd.n, c.h.lanes);
+        (const T*)E.d_lam.p, (const int*)c.varmap_adj.p, d_user_out, NA, c.h.n_inst, (int)E.E, (int)P, (int)E.bwd.n, c.h.lanes, pairs ? 2 : 1);
     ++E.last_launches;
     if (carry) {
       // d_bwd_QinitCond <- running adjoint state (src/__GpuDriver.cu:743); d_fwd_Q keeps the last recomputed state
@@ -1246,7 +1262,7 @@ void solve_gradient(pasif_engine& E, uint32_t save, T* d_user_out) {
       c.lam_dirty = true;
       const long long ftot = (long long)NF * P;
       scatter_user_kernel<T><<<(unsigned)((ftot + threads - 1) / threads), threads, 0, E.stream>>>(
-          (const T*)q_end, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, NF, c.h.n_inst, (int)E.E, (int)P, (int)E.fwd.n, c.h.lanes);
+          (const T*)q_end, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, NF, c.h.n_inst, (int)E.E, (int)P, (int)E.fwd.n, c.h.lanes, pairs ? 2 : 1);
       ++E.last_launches;
     }
   }
@@ -1275,9 +1291,9 @@ void gradient_entry(pasif_engine& E, uint32_t save, double* out, uint64_t n_out,
         const long long tot = (long long)c.h.fwd.N * c.n_traj;
         E.d_q0.reserve((size_t)std::max<long long>(tot, 1) * sizeof(T));
         init_state_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>((const T*)c.ic.p, (T*)E.d_q0.p, c.h.fwd.N, c.h.n_inst,
-                                                                                   (int)E.E, (int)c.n_traj, c.h.lanes);
+                                                                                   (int)E.E, (int)c.n_traj, c.h.lanes, 1);
         scatter_user_kernel<T><<<(unsigned)((tot + 255) / 256), 256, 0, E.stream>>>(
-            (const T*)E.d_q0.p, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, c.h.fwd.N, c.h.n_inst, (int)E.E, (int)c.n_traj, (int)E.fwd.n, c.h.lanes);
+            (const T*)E.d_q0.p, (const int*)c.varmap.p, (T*)E.d_fwd_cur.p, c.h.fwd.N, c.h.n_inst, (int)E.E, (int)c.n_traj, (int)E.fwd.n, c.h.lanes, 1);
         E.last_launches += 2;
       }
   }
@@ -1592,6 +1608,8 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->unit_on = (v == "on" || v == "1");
   } else if (k == "pair") {
     e->pair_on = (v == "on" || v == "1");
+  } else if (k == "lane_pair") {
+    e->lane_pair_on = (v == "on" || v == "1");
   } else if (k == "pair_regs") {
     e->pair_regs = std::atoi(v.c_str());
   } else if (k == "aot") {

@@ -371,7 +371,9 @@ struct LaneSplitReport {
 };
 
 // One attempt with a given group width and unit order.  Returns false when the split is not viable.
-inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int reg_budget, double min_eff, ClassData& out,
+// pair: the class will run on the fp32 pair kernels (rk4_kernels.cuh, W = 2) -- every state / stage / halo slot is a 64-bit
+// register pair, the coefficients stay scalars
+inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int reg_budget, double min_eff, bool pair, ClassData& out,
                            LaneSplitReport& rep) {
   using namespace lane_detail;
   const Pattern& F = c.fwd;
@@ -481,9 +483,9 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   rep.halo_adj = c.joint ? (int)sa.pat.hx_slot.size() : 0;
   rep.halo_p = c.joint ? (int)sa.pat.hp_slot.size() : 0;
   rep.nv = c.joint ? (int)sa.pat.nv.size() : 0;
-  const int words = tbytes / 4;
-  const int regs_f = (rep.nc_fwd + 4 * fa.R + rep.halo_fwd) * words + 24;
-  const int regs_a = c.joint ? (rep.nc_adj + 4 * aa.R + rep.halo_adj + 3 * ((int)sa.pat.nv.size() + rep.halo_p)) * words + 24 : 0;
+  const int words = tbytes / 4, sw = pair ? 2 * words : words;      // registers per coefficient / per state slot
+  const int regs_f = rep.nc_fwd * words + (4 * fa.R + rep.halo_fwd) * sw + 24;
+  const int regs_a = c.joint ? rep.nc_adj * words + (4 * aa.R + rep.halo_adj + 3 * ((int)sa.pat.nv.size() + rep.halo_p)) * sw + 24 : 0;
   rep.regs_est = std::max(regs_f, regs_a);
   const double real = (double)F.nc() + (c.joint ? (double)c.adj.nc() : 0.0);
   rep.efficiency = real / ((double)G * (double)(rep.nc_fwd + rep.nc_adj));
@@ -496,8 +498,9 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
   {
     // static shared memory of the halo exchange: 2 buffers x published slots x CTA width, per exchange kind
     const size_t cta = (size_t)std::max(G, 128);
-    const size_t smem_f = 2 * sf.pat.pub_slot.size() * cta * (size_t)tbytes;
-    const size_t smem_a = c.joint ? 2 * (sa.pat.pub_slot.size() + sa.pat.ppub_slot.size()) * cta * (size_t)tbytes : 0;
+    const size_t ebytes = (size_t)tbytes * (pair ? 2 : 1);            // a published slot is a pair in the pair kernels
+    const size_t smem_f = 2 * sf.pat.pub_slot.size() * cta * ebytes;
+    const size_t smem_a = c.joint ? 2 * (sa.pat.pub_slot.size() + sa.pat.ppub_slot.size()) * cta * ebytes : 0;
     if (std::max(smem_f, smem_a) > 40 * 1024) { rep.why = "halo exchange would need more than 40 KB of shared memory"; return false; }
   }
   // a lane that reads more operands from other lanes than it owns is a dense coupling: the exchange would dominate, and
@@ -584,7 +587,8 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
 
 // Tries group widths from narrow to wide and both unit orders; keeps the first width that fits the register budget,
 // with the order that gives the smaller common pattern.
-inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, double min_eff, ClassData& out, LaneSplitReport& rep) {
+inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, double min_eff, ClassData& out, LaneSplitReport& rep,
+                       bool pair = false) {
   const long long terms = (long long)c.fwd.nc() + c.adj.nc();
   const long long rows = (long long)c.fwd.N + c.adj.N;
   if (terms > 64 * rows) { rep.why = "operator too dense for a lane split (" + std::to_string(terms / std::max<long long>(rows, 1)) + " terms per row)"; return false; }
@@ -595,10 +599,10 @@ inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_bu
     for (int cm = 0; cm < 2; ++cm) {
       ClassData cand;
       LaneSplitReport r;
-      if (!lane_split_try(c, G, cm != 0, tbytes, reg_budget, min_eff, cand, r)) { if (!have) brep = r; continue; }
+      if (!lane_split_try(c, G, cm != 0, tbytes, reg_budget, min_eff, pair, cand, r)) { if (!have) brep = r; continue; }
       if (!have || r.nc_fwd + r.nc_adj < brep.nc_fwd + brep.nc_adj) { best = std::move(cand); brep = r; have = true; }
     }
-    if (have) { out = std::move(best); rep = brep; return true; }
+    if (have) { out = std::move(best); out.lane_pair = pair; rep = brep; return true; }
     rep = brep;
   }
   return false;

@@ -86,6 +86,7 @@ struct Pattern {
 struct ClassData {
   bool joint = false;
   int lanes = 1;     // > 1: lane-block class (lane_split.hpp): n_inst counts VIRTUAL instances (instance * lanes + lane)
+  bool lane_pair = false;   // lane-block class sized for the fp32 pair kernels (two trajectories per thread: state slots count twice)
   Pattern fwd;  // forward pattern (joint: forward part of the joint component)
   Pattern adj;  // joint only
   uint64_t hash = 0;

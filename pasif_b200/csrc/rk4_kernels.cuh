@@ -244,17 +244,20 @@ PASIF_DEV void rk4_forward_step(V (&q)[P::N], const T (&c)[P::NC > 0 ? P::NC : 1
 
 // ------------------------------------------------------------------------------------------------ forward kernel
 // PF: forward pattern.  DV: list of forward variables written by the dense save (DV::NV may be 0).
-// W: trajectories per thread (2: packed fp32 pairs, G == 1 and E even; the dense save of a pair is ONE vector of
-// 2 NV values in [variable][half] order -- written and read only by the pair kernels of the same class).
+// W: trajectories per thread (2: packed fp32 pairs, E even; the dense save of a pair is ONE vector of 2 NV values in
+// [variable][half] order -- written and read only by the pair kernels of the same class).  Lane-block classes (G > 1)
+// pair the same lane of two consecutive trajectories; their halo exchange then moves 8-byte pairs.
 template <typename T, class PF, class DV, int W = 1>
 PASIF_DEV void forward_body(const FwdArgs<T>& a) {
   typedef typename Vec<T, W>::type V;
-  static_assert(W == 1 || PF::G == 1, "two trajectories per thread: one-thread classes only");
-  const int p = (blockIdx.x * blockDim.x + threadIdx.x) * W;     // first trajectory of the thread
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = tix * W;                           // first of the thread's W consecutive slots in the trajectory-minor arrays
   if (p >= a.n_traj) return;                       // lane-block classes: whole groups leave together (n_traj % G == 0)
   constexpr int G = PF::G;
-  const int lane = p & (G - 1);
-  const int traj = p / G;
+  // thread -> (lane, trajectory): G consecutive threads are the lanes of one trajectory (W = 2: of the trajectory PAIR
+  // 2j, 2j + 1, whose two values sit side by side in every array -- slot p = (j * G + lane) * 2 + half)
+  const int lane = tix & (G - 1);
+  const int traj = (tix / G) * W;
   const int e = traj % a.E;
   const int inst = (traj / a.E) * G + lane;       // virtual instance (G == 1: the instance itself)
   constexpr int N = PF::N;
@@ -386,12 +389,12 @@ PASIF_DEV void forward_body(const FwdArgs<T>& a) {
 template <typename T, class PA, int W = 1>
 PASIF_DEV void backward_body(const BwdArgs<T>& a) {
   typedef typename Vec<T, W>::type V;
-  static_assert(W == 1 || PA::G == 1, "two trajectories per thread: one-thread classes only");
-  const int p = (blockIdx.x * blockDim.x + threadIdx.x) * W;
+  const int tix = blockIdx.x * blockDim.x + threadIdx.x;
+  const int p = tix * W;                           // slot of the thread in the trajectory-minor arrays (see forward_body)
   if (p >= a.n_traj) return;
   constexpr int G = PA::G;
-  const int lane = p & (G - 1);
-  const int inst = (p / G / a.E) * G + lane;       // virtual instance (G == 1: the instance itself)
+  const int lane = tix & (G - 1);
+  const int inst = ((tix / G) * W / a.E) * G + lane;   // virtual instance (G == 1: the instance itself)
   constexpr int N = PA::N;
   constexpr int NC = PA::NC > 0 ? PA::NC : 1;
   constexpr int NV = PA::NV > 0 ? PA::NV : 1;
