@@ -38,6 +38,24 @@ for axis, n_sys in (("excitations", 1), ("systems", 4)):
     err = float(np.max(np.abs(red - full)) / np.max(np.abs(full)))
     assert err < 1e-13, (axis, err)
     out[axis] = err
+# presharded: every rank hands over only its own block of systems (weak scaling); offsets come from an all-gather
+rank = dist.get_rank()
+blocks = [[wl.jitter(wl.fit8_system(), np.random.default_rng(50 + r)) for _ in range(2 + r)] for r in range(2)]
+jblocks = [[wl.jitter(wl.fit8_jacobian(), np.random.default_rng(60 + r)) for _ in range(2 + r)] for r in range(2)]
+exc = wl.random_sine_excitations(4, 250, 16000, seed=3)
+sp = ShardedPASIf([np.array(r) for r in exc], 16000, 0, driver_cls=CRecordingDriver, presharded=True)
+sp.setSystems(*wl.to_frontend_args(blocks[rank], mod))
+sp.setJacobian(*wl.to_frontend_args(jblocks[rank], mod, with_psi=True))
+assert sp.n_systems == 5 and sp._sys_range == ((0, 2) if rank == 0 else (2, 5)) and sp.n_adj_global == 60
+assert sp.adj_slice == ((0, 24) if rank == 0 else (24, 60))
+red = sp.getGradientReduced()
+one = frontend.make_frontend(CRecordingDriver)([np.array(r) for r in exc], 16000, 0)
+one.setSystems(*wl.to_frontend_args(blocks[0] + blocks[1], mod))
+one.setJacobian(*wl.to_frontend_args(jblocks[0] + jblocks[1], mod, with_psi=True))
+full = np.asarray(one.getGradient()).reshape(4, -1).sum(axis=0)
+err = float(np.max(np.abs(red - full)) / np.max(np.abs(full)))
+assert err < 1e-13, ("presharded", err)
+out["presharded"] = err
 if dist.get_rank() == 0:
     print("SHARDED_OK", out)
 dist.destroy_process_group()
@@ -60,6 +78,14 @@ def test_block_partition_covers_everything():
             assert all(parts[i][1] == parts[i + 1][0] for i in range(w - 1))
             sizes = [b - a for a, b in parts]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_choose_axis():
+    from pasif_b200.sharded import choose_axis
+    import pytest
+    assert choose_axis(8, 2, 8) == "systems" and choose_axis(1, 64, 8) == "excitations" and choose_axis(3, 64, 2) == "systems"
+    with pytest.raises(ValueError):
+        choose_axis(3, 5, 8)
 
 
 def test_sharded_gradient_allreduce_gloo_world2(tmp_path):
