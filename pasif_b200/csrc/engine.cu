@@ -34,6 +34,7 @@
 #include "large_kernels.cuh"
 #include "stage_kernels.cuh"
 #include "stage_tcgen05.cuh"
+#include "stage_stream.cuh"
 
 using namespace pasif_host;
 
@@ -511,8 +512,11 @@ struct pasif_engine {
   cudaEvent_t ev_rec[2] = {nullptr, nullptr}, ev_bwd[2] = {nullptr, nullptr};
   // dense-operator path: the batch is cut into `stage_nparts` parts, each with its own stream, so that the tensor-bound
   // GEMM of one part overlaps the HBM-bound update of another (part 0 runs on `stream`)
-  int stage_nparts = 4;
+  int stage_nparts = 2;
   int update_u = 4;                              // trajectories per thread of the dense-operator path's update kernel
+  bool update_stream = true;                     // dense-operator path: persistent bulk-copy-pipelined update kernel (stage_stream.cuh)
+  int stream_tt = 0;                             // ... trajectories per tile (0: 4 in fp32, 2 in fp64)
+  int stream_ctas = 2;                           // ... resident CTAs per SM the grid is sized for
   std::vector<cudaStream_t> part_streams;
   std::vector<cudaEvent_t> part_events;
   bool overlap = true;
@@ -1574,6 +1578,16 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->stage_nparts = n;
   } else if (k == "update_u") {
     e->update_u = std::atoi(v.c_str());
+  } else if (k == "update_stream") {
+    e->update_stream = (v == "on" || v == "1");
+  } else if (k == "stream_tt") {
+    const int t = std::atoi(v.c_str());
+    if (t != 0 && t != 2 && t != 4 && t != 8) throw std::runtime_error("stream_tt must be 0 (auto), 2, 4 or 8");
+    e->stream_tt = t;
+  } else if (k == "stream_ctas") {
+    const int t = std::atoi(v.c_str());
+    if (t < 1 || t > 2) throw std::runtime_error("stream_ctas must be 1 or 2");
+    e->stream_ctas = t;
   } else if (k == "bwd_priority") {
     // scheduling priority of the adjoint stream against the recompute stream: "high" | "low" | "default"
     if (e->host_only) return 0;

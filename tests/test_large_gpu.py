@@ -243,3 +243,39 @@ def test_dense_operator_offsite_nonlinear_terms(variant, prec):
     assert rel_err(a["trajectory"], b["trajectory"]) < TOL_FWD[prec]
     assert close(a["gradient"], b["gradient"], na, prec, TOL_ADJ)
 
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("shape", ["small_ragged", "two_parts", "replicas_nonuniform", "config4_rows", "many_tiles"])
+def test_stream_update_is_bit_identical(shape, prec):
+    """The persistent bulk-copy-pipelined update kernel (stage_stream.cuh, the default) does the arithmetic of the
+    per-thread update kernel (update_stream=off) term by term in the same order: every output is equal bit for bit --
+    ragged batches (E not a multiple of the tile of trajectories), several parts on their own streams, instances with
+    their own coefficients whose boundaries fall inside a tile, and the full 514-state system of BASELINE config 4;
+    tiles of 2, 4 and 8 trajectories, one or two CTAs per SM."""
+    if shape == "small_ragged":
+        case = chain_case(40, True, E=11, L=200)
+    elif shape == "two_parts":
+        case = chain_case(32, True, E=301, L=40)
+    elif shape == "replicas_nonuniform":
+        base = wl.chain_system(40, dense=True, seed=3)
+        rng = np.random.default_rng(11)
+        systems = [wl.jitter_nonlinear(base, rng) for _ in range(3)]
+        case = dict(systems=systems, jacobians=[wl.chain_jacobian(s, 3) for s in systems],
+                    excitations=wl.random_sine_excitations(50, 120, 16000, seed=6), sample_rate=16000, numsteps=0, interp=None,
+                    traj_save_steps=40)
+    elif shape == "many_tiles":
+        # several tiles per CTA: the buffer ring of the kernel wraps (the grid holds at most 2 CTAs per SM)
+        case = chain_case(32, True, E=4800, L=6)
+        case["traj_save_steps"] = None
+    else:
+        case = chain_case(256, True, E=130, L=16)
+        case["traj_save_steps"] = None
+    ref = run_case(capi.engine_class(prec), case, options={"update_stream": "off"})
+    assert ref["_p"]._query("large_stage_classes") >= 1
+    for tt, ctas in (("0", "2"), ("2", "2"), ("4", "2"), ("0", "1"), ("8", "1")):
+        if shape == "config4_rows" and tt == "2":
+            continue
+        a = run_case(capi.engine_class(prec), case, options={"update_stream": "on", "stream_tt": tt, "stream_ctas": ctas})
+        for key in ("amplitudes", "trajectory", "gradient"):
+            if key in ref and ref[key] is not None:
+                assert np.array_equal(a[key], ref[key]), (key, tt)
