@@ -517,6 +517,10 @@ struct pasif_engine {
   bool update_stream = true;                     // dense-operator path: persistent bulk-copy-pipelined update kernel (stage_stream.cuh)
   int stream_tt = 0;                             // ... trajectories per tile (0: 4 in fp32, 2 in fp64)
   int stream_ctas = 2;                           // ... resident CTAs per SM the grid is sized for
+  int stream_smem_kb = 0;                        // ... shared memory of one CTA (0: the SM's share); with tc_stages: room for a GEMM CTA beside it
+  int stream_grid = 0;                           // ... CTAs per SM in the grid (0: stream_ctas)
+  int tc_stages = 0;                             // fused-split GEMM: pipeline stages (0: as many as fit an SM)
+  bool stage_dephase = false;                    // parts start one GEMM apart, so GEMMs run beside the neighbour's updates
   std::vector<cudaStream_t> part_streams;
   std::vector<cudaEvent_t> part_events;
   bool overlap = true;
@@ -540,6 +544,8 @@ struct pasif_engine {
   std::string lane_reject;                       // why the last large class was not split
   long long large_classes = 0, large_gemm_classes = 0, large_stage_classes = 0, gemm_launches = 0;
   bool tcgen05_on = true;                        // fp32 stage GEMM on tcgen05/TMEM/TMA (else the mma.sync 3xTF32 kernel)
+  bool tc_pair = true;                           // fused-split GEMM on CTA pairs (tcgen05.mma.cta_group::2: every CTA holds half of the K' tile)
+  int tc_pair_nt = 2;                            // ... row tiles of 256 per pair (2 when the band is a multiple of 512 rows)
   bool tc_multicast = false;                     // fused-split GEMM on clusters of two CTAs with the K' tile multicast (experimental)
   bool stage_direct = true;                      // dense-operator path: the state array is the stage vector of stage 1 (stage 4 writes one array)
   int tc_bk = 16;                                // fused-split GEMM: floats per k-block (16: 64-byte swizzle, twice the pipeline stages; 32: r01)
@@ -1606,6 +1612,28 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->tc_bk = b;
   } else if (k == "tc_bn") {
     e->tc_bn = std::atoi(v.c_str());
+  } else if (k == "stream_smem_kb") {
+    const int t = std::atoi(v.c_str());
+    if (t != 0 && (t < 16 || t > 226)) throw std::runtime_error("stream_smem_kb must be 0 (auto) or 16..226");
+    e->stream_smem_kb = t;
+  } else if (k == "stream_grid") {
+    const int t = std::atoi(v.c_str());
+    if (t < 0 || t > 4) throw std::runtime_error("stream_grid must be 0 (auto) .. 4");
+    e->stream_grid = t;
+  } else if (k == "tc_stages") {
+    const int t = std::atoi(v.c_str());
+    if (t != 0 && (t < 2 || t > 6)) throw std::runtime_error("tc_stages must be 0 (auto) or 2..6");
+    e->tc_stages = t;
+  } else if (k == "pdl") {
+    g_stage_pdl = (v == "on" || v == "1");              // (process-wide: programmatic dependent launch of the dense-operator kernels)
+  } else if (k == "stage_dephase") {
+    e->stage_dephase = (v == "on" || v == "1");
+  } else if (k == "tc_pair") {
+    e->tc_pair = (v == "on" || v == "1");
+  } else if (k == "tc_pair_nt") {
+    const int t = std::atoi(v.c_str());
+    if (t != 1 && t != 2) throw std::runtime_error("tc_pair_nt must be 1 or 2");
+    e->tc_pair_nt = t;
   } else if (k == "tc_multicast") {
     e->tc_multicast = (v == "on" || v == "1");
   } else if (k == "tc_split") {

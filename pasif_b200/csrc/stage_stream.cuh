@@ -66,6 +66,8 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncthreads();
+  pasif_tc::pdl_launch_dependents();
+  pasif_tc::pdl_wait();                                 // (programmatic dependent launch: the predecessor has completed from here on)
 
   if (r >= NR) {
     // ---- producer: lane 0 of the first warp without rows

@@ -153,6 +153,11 @@ def test_wide_tile_gemm_is_bit_identical(shape):
     # 16-float k-blocks (64-byte swizzle, twice the pipeline stages): the same products in the same order
     assert np.array_equal(capi.debug_gemm(kd, x, "f32", 5), y_fs)
     assert np.array_equal(capi.debug_gemm(kd, x, "f32", 6), y_fs)
+    # CTA pairs (tcgen05.mma.cta_group::2, M = 256 trajectories, every CTA holds half of the K' tile): one 256-row tile per
+    # pair, and two tiles that share the X tile when the rows are a multiple of 512
+    assert np.array_equal(capi.debug_gemm(kd, x, "f32", 7), y_fs)
+    if N % 512 == 0:
+        assert np.array_equal(capi.debug_gemm(kd, x, "f32", 8), y_fs)
 
 
 def test_config4_size_dense_chain_matches_oracle_f32():
