@@ -270,7 +270,8 @@ __device__ __forceinline__ void epilogue_bulk_store(uint32_t tmem_d, int warp, i
       }
     }
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  // shared memory must outlive the reads of the bulk stores; their global writes complete with the grid
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 template <int TC_BN, int BK = TC_BK, int PROBE = 0>
