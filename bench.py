@@ -432,6 +432,8 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
             ar_ms += r_ms
             per_step += [d_ms, r_ms]
             launches += int(p._query("last_launches"))
+    # dense-operator path: host time the last gradient spent queueing its launches (it must stay well below the device time)
+    enqueue_ms = p._query("stage_enqueue_us") * 1e-3 if (not job.forward_only and _has_query(p, "stage_enqueue_us")) else 0.0
     ctx.barrier()
     wall_grad = time.time() - wall0
     # ---------------- per-kernel device times: more steps with profile=on (a CUDA-event pair around every hot-kernel
@@ -673,6 +675,8 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
                          "note": hbm_note, "peak_source": "MEASURED_PEAKS.json" if ctx.peaks else "fallback"},
         "wall_s_grad_steps": wall_grad,
     })
+    if stage and enqueue_ms > 0:
+        entry["host_enqueue_ms_per_step"] = enqueue_ms
     if do_e2e:
         entry["e2e"] = {"value": tot_pairs * e2e_steps / e2e_t, "unit": "gradient evals/s", "h2d_bytes_per_step": int(p._query("last_h2d_bytes")),
                         "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,

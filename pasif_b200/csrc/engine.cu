@@ -18,6 +18,7 @@
 #include <time.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -519,6 +520,10 @@ struct pasif_engine {
   int stream_ctas = 2;                           // ... resident CTAs per SM the grid is sized for
   int stream_smem_kb = 0;                        // ... shared memory of one CTA (0: the SM's share); with tc_stages: room for a GEMM CTA beside it
   int stream_grid = 0;                           // ... CTAs per SM in the grid (0: stream_ctas)
+  int stream_grid_ctas = 0;                      // ... or the absolute number of CTAs (0: per SM as above)
+  bool stream_dynamic = false;                   // ... tiles drawn from a counter instead of a fixed share per CTA
+  long long stage_enqueue_us = 0;                // host time the last dense-operator gradient spent queueing launches
+  DevBuf stage_sched;                            // ... the counters: (next tile, finished CTAs) per part
   int tc_stages = 0;                             // fused-split GEMM: pipeline stages (0: as many as fit an SM)
   bool stage_dephase = false;                    // parts start one GEMM apart, so GEMMs run beside the neighbour's updates
   std::vector<cudaStream_t> part_streams;
@@ -1447,7 +1452,7 @@ void pasif_destroy(pasif_engine* e) {
     free_classes(e->fwd_classes);
     free_classes(e->joint_classes);
     for (DevBuf* b : {&e->d_tail, &e->d_raw, &e->d_exc, &e->d_user, &e->d_traj, &e->d_ckpt, &e->d_dense, &e->d_dense2, &e->d_lam, &e->d_red,
-                      &e->d_fwd_cur, &e->d_q0, &e->d_qend}) b->release();
+                      &e->d_fwd_cur, &e->d_q0, &e->d_qend, &e->stage_sched}) b->release();
     for (int i = 0; i < 2; ++i) {
       if (e->ev_rec[i]) cudaEventDestroy(e->ev_rec[i]);
       if (e->ev_bwd[i]) cudaEventDestroy(e->ev_bwd[i]);
@@ -1620,6 +1625,12 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     const int t = std::atoi(v.c_str());
     if (t < 0 || t > 4) throw std::runtime_error("stream_grid must be 0 (auto) .. 4");
     e->stream_grid = t;
+  } else if (k == "stream_grid_ctas") {
+    const int t = std::atoi(v.c_str());
+    if (t < 0 || t > 4096) throw std::runtime_error("stream_grid_ctas must be 0 (auto) .. 4096");
+    e->stream_grid_ctas = t;
+  } else if (k == "stream_dynamic") {
+    e->stream_dynamic = (v == "on" || v == "1");
   } else if (k == "tc_stages") {
     const int t = std::atoi(v.c_str());
     if (t != 0 && (t < 2 || t > 6)) throw std::runtime_error("tc_stages must be 0 (auto) or 2..6");
@@ -1791,6 +1802,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "large_gemm_classes") *value = (double)e->large_gemm_classes;
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
+  else if (k == "stage_enqueue_us") *value = (double)e->stage_enqueue_us;
   else if (k == "stage_direct") *value = stage_direct(*e, e->dtype == PASIF_F32 ? 4 : 8) ? 1.0 : 0.0;
   else if (k.rfind("stage_band_", 0) == 0) {
     // rows / columns of K' that go through the per-stage GEMM of the (first) dense-operator class:

@@ -35,6 +35,10 @@ struct StreamArgs {
   // offsets (in values of T) of the arrays inside one buffer; o_x == o_q when the state array is the stage vector
   // (stage 1 of the stage_direct scheme), o_pa == o_x for a forward system (the set point is the stage vector)
   int o_y, o_q, o_s, o_x, o_pa, o_pb, buf_elems;
+  // dynamic tile scheduling (nullptr: tile = blockIdx.x + k * gridDim.x): sched[0] = next tile, sched[1] = CTAs that have
+  // drawn their last tile; the last of them resets both for the next launch on the same stream.  A CTA that starts late
+  // (its SM was busy with the GEMM of another part) then takes what is left instead of a fixed share of the batch.
+  int* sched;
 };
 constexpr int STREAM_MAXBUF = 4;
 
@@ -52,6 +56,7 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
   extern __shared__ __align__(128) unsigned char ss_raw[];
   uint64_t* full = reinterpret_cast<uint64_t*>(ss_raw);                 // [STREAM_MAXBUF]
   uint64_t* empty = full + STREAM_MAXBUF;                               // [STREAM_MAXBUF]
+  int* tile_of = reinterpret_cast<int*>(empty + STREAM_MAXBUF);         // [STREAM_MAXBUF] tile in each buffer (-1: no more tiles)
   T* bufs = reinterpret_cast<T*>(ss_raw + 128);
   const UpdArgs<T>& u = a.u;
   const Tables& tb = u.tb;
@@ -81,8 +86,20 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
     if (HALF) total += p_bytes;
     int buf = 0;
     uint32_t phase = 0;
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += stride) {
+    for (int tile = blockIdx.x;; tile += stride) {
       pasif_tc::mbar_wait(&empty[buf], phase ^ 1);                       // first pass over the buffers: free at once
+      if (a.sched) tile = atomicAdd(a.sched, 1);
+      if (tile >= a.n_tiles) {
+        // end marker for the row warps; with dynamic scheduling the last CTA to get here re-arms the counters
+        tile_of[buf] = -1;
+        pasif_tc::mbar_arrive(&full[buf]);
+        if (a.sched) {
+          __threadfence();
+          if (atomicAdd(a.sched + 1, 1) == (int)gridDim.x - 1) { a.sched[0] = 0; a.sched[1] = 0; __threadfence(); }
+        }
+        break;
+      }
+      tile_of[buf] = tile;
       const long long p0 = (long long)tile * TT;
       T* B = bufs + (size_t)buf * a.buf_elems;
       pasif_tc::mbar_expect_tx(&full[buf], total);
@@ -122,7 +139,11 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
 
   int buf = 0;
   uint32_t phase = 0;
-  for (int tile = blockIdx.x; tile < a.n_tiles; tile += stride) {
+  for (;;) {
+    // the producer names the tile of a buffer before it arrives on (or hands the loads to) the buffer's barrier
+    pasif_tc::mbar_wait(&full[buf], phase);
+    const int tile = tile_of[buf];
+    if (tile < 0) break;
     const long long p0 = (long long)tile * TT;
     const int nb = (int)min((long long)TT, (long long)u.n_traj - p0);
     const unsigned pg0 = (unsigned)(u.p_base + p0);
@@ -136,7 +157,6 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
         if (b + 1 < nb) { if (++e == E) { e = 0; ++i; } }                // slots past the batch stay on the last trajectory
       }
     }
-    // everything that does not depend on the tile's data is requested before the wait
     const T* __restrict__ vu = v0 + inst0 * cs;
     if (UNI && inst0 != cur_inst) {
       cur_inst = inst0;
@@ -147,7 +167,6 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
     }
     auto coef = [&](int b, int o) -> T { return __ldg(v0 + ib[b] * cs + o); };
 
-    pasif_tc::mbar_wait(&full[buf], phase);
     const T* __restrict__ B = bufs + (size_t)buf * a.buf_elems;
     const T* __restrict__ Xs = B + a.o_x;
     const T* __restrict__ Ps = B + a.o_pa;

@@ -291,7 +291,7 @@ def test_gemm_launch_variants_are_bit_identical():
     (tcgen05.mma.cta_group::2, the default when the part is a multiple of 256 trajectories and the band a multiple of 256
     rows; two row tiles per pair for the 512-row adjoint band) or single CTAs, programmatic dependent launch on / off, fewer
     pipeline stages with a shared-memory budget for the update kernel that leaves room for a GEMM CTA on the same SM, parts
-    that start one GEMM apart.  Amplitudes and gradient of the full 514-state chain are equal bit for bit in all of them."""
+    that start one GEMM apart, tiles of the update kernel drawn from a counter instead of a fixed share per CTA.  Amplitudes and gradient of the full 514-state chain are equal bit for bit in all of them."""
     case = chain_case(256, True, E=512, L=6)
     case["traj_save_steps"] = None
     ref = run_case(capi.engine_class("f32"), case, options={"tc_pair": "off", "pdl": "off"})
@@ -301,7 +301,9 @@ def test_gemm_launch_variants_are_bit_identical():
                      {"tc_pair": "on", "tc_pair_nt": "1", "pdl": "off"},
                      {"tc_pair": "off", "pdl": "on", "stage_parts": "1"},
                      {"tc_pair": "off", "tc_stages": "3", "stream_smem_kb": "80", "stream_grid": "1", "stage_dephase": "on", "stage_parts": "4"},
-                     {"tc_pair": "off", "tc_stages": "2", "stream_smem_kb": "128", "stream_grid": "1", "stage_parts": "2"}):
+                     {"tc_pair": "off", "tc_stages": "2", "stream_smem_kb": "128", "stream_grid": "1", "stage_parts": "2"},
+                     {"stream_dynamic": "on", "stream_grid_ctas": "168", "stage_dephase": "on"},
+                     {"stream_dynamic": "on", "stage_parts": "3"}):
             a = run_case(capi.engine_class("f32"), case, options=opts)
             for key in ("amplitudes", "gradient"):
                 assert np.array_equal(a[key], ref[key]), (key, opts)
