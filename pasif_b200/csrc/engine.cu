@@ -532,6 +532,7 @@ struct pasif_engine {
   std::string err;
   bool compat_clean = false, jit_on = true, gemm_on = true;
   int large_threshold = 48;                      // components with more coupled variables use the lane-block / tile kernels
+  int lanes_min = 8;                             // narrowest thread group the split tries (2 / 4: small systems of a small batch, see DESIGN "Small batches")
   int lanes_max = 1024;                          // widest thread group of the lane-block split (0: off)
   bool unit_on = true;                           // register kernels: K terms with coefficient exactly 1 become additions
   bool pair_on = true;                           // fp32 one-thread classes: two trajectories per thread (packed FFMA2)
@@ -824,7 +825,7 @@ void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<De
         // fp32 with an even number of excitations: the class will run two trajectories per thread (packed FFMA2), so the
         // split is sized with every state slot counted twice (it then picks a group twice as wide)
         const bool pair_mode = sizeof(T) == 4 && E.pair_on && E.lane_pair_on && E.E % 2 == 0;
-        ok = lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, E.lane_min_eff, split, rep, pair_mode);
+        ok = lane_split(dc.h, (int)sizeof(T), E.lanes_max, E.lane_regs, E.lane_min_eff, split, rep, pair_mode, E.lanes_min);
       } catch (const std::exception& ex) {       // a split that fails its own check is never used: the other paths take over
         rep.why = ex.what();
         ++E.lane_selfcheck_failures;
@@ -1675,6 +1676,10 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->lane_minb_fwd = std::atoi(v.c_str());
   } else if (k == "lane_minb_bwd") {
     e->lane_minb_bwd = std::atoi(v.c_str());
+  } else if (k == "lanes_min") {
+    const int t = std::atoi(v.c_str());
+    if (t != 2 && t != 4 && t != 8 && t != 16 && t != 32) throw std::runtime_error("lanes_min must be 2, 4, 8, 16 or 32");
+    e->lanes_min = t;
   } else if (k == "one_thread_regs") {
     e->one_thread_regs = std::atoi(v.c_str());
   } else if (k == "lane_min_eff") {
@@ -1866,6 +1871,14 @@ int pasif_debug_jit_log(pasif_engine* e, const char* arch, char* buf, uint64_t c
       if (g_nvrtc.CreateProgram(&prog, src.c_str(), "pasif_jit.cu", 0, nullptr, nullptr) != 0) throw std::runtime_error("nvrtcCreateProgram failed");
       const char* opts[] = {a.c_str(), "-std=c++17", "-lineinfo", "--ptxas-options=-v"};
       const int rc = g_nvrtc.CompileProgram(prog, 4, opts);
+      if (const char* dump = std::getenv("PASIF_B200_DUMP_CUBIN")) {      // (debug: the cubin beside the log, for cuobjdump -sass)
+        size_t cn = 0;
+        if (rc == 0 && g_nvrtc.GetCUBINSize(prog, &cn) == 0 && cn) {
+          std::vector<char> cb(cn);
+          g_nvrtc.GetCUBIN(prog, cb.data());
+          std::ofstream(std::string(dump) + "/" + c.h.name + "_lanes" + std::to_string(c.h.lanes) + ".cubin", std::ios::binary).write(cb.data(), (std::streamsize)cn);
+        }
+      }
       size_t n = 0;
       g_nvrtc.GetProgramLogSize(prog, &n);
       std::string log(n, '\0');

@@ -588,11 +588,11 @@ inline bool lane_split_try(const ClassData& c, int G, bool cm, int tbytes, int r
 // Tries group widths from narrow to wide and both unit orders; keeps the first width that fits the register budget,
 // with the order that gives the smaller common pattern.
 inline bool lane_split(const ClassData& c, int tbytes, int max_lanes, int reg_budget, double min_eff, ClassData& out, LaneSplitReport& rep,
-                       bool pair = false) {
+                       bool pair = false, int min_lanes = 8) {
   const long long terms = (long long)c.fwd.nc() + c.adj.nc();
   const long long rows = (long long)c.fwd.N + c.adj.N;
   if (terms > 64 * rows) { rep.why = "operator too dense for a lane split (" + std::to_string(terms / std::max<long long>(rows, 1)) + " terms per row)"; return false; }
-  for (int G = 8; G <= max_lanes; G *= 2) {
+  for (int G = std::max(2, min_lanes); G <= max_lanes; G *= 2) {
     ClassData best;
     LaneSplitReport brep;
     bool have = false;

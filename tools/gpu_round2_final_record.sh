@@ -1,3 +1,6 @@
+#!/bin/bash
+# Final record of round 2 in one gpurun call on one B200: GPU suite, memcheck of the dense-operator GEMM variants, smoke(), reference
+# arm and the default bench line (everything lands in gpurun_out/r02ag_*).
 mkdir -p gpurun_out
 timeout 900 python -m pytest tests -m gpu -x -q > gpurun_out/r02ag_pytest.log 2>&1; tail -2 gpurun_out/r02ag_pytest.log
 timeout 600 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest tests/test_large_gpu.py -x -q -m gpu -k "wide_tile or launch_variants or two_overlapping" > gpurun_out/r02ag_memcheck.log 2>&1
