@@ -309,3 +309,20 @@ def test_gemm_launch_variants_are_bit_identical():
                 assert np.array_equal(a[key], ref[key]), (key, opts)
     finally:
         run_case(capi.engine_class("f32"), chain_case(8, True, E=4, L=4), options={"pdl": "on"})   # (process-wide switch back to its default)
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+def test_dense_operator_exact_schedule_in_one_chunk(prec):
+    """compat=clean on the dense-operator path: when the forward states of all steps fit the free device memory the run is
+    ONE chunk (one forward sweep that writes every state, no checkpoints, no recompute); with tail_budget_gb=0 it is the
+    square-root schedule (sweep with checkpoints + recompute of every chunk).  Recomputed states equal swept states, so the
+    gradients are equal bit for bit -- and both match the oracle's exact schedule."""
+    case = chain_case(40, True, E=24, L=90)
+    one = run_case(capi.engine_class(prec, "clean"), case)
+    sq = run_case(capi.engine_class(prec, "clean"), case, options={"tail_budget_gb": "0"})
+    assert one["_p"]._query("large_stage_classes") >= 1
+    assert one["_p"]._query("stored_chunks") == one["_p"]._query("chunks") == 9        # 89 steps in chunks of ceil(sqrt 89) = 10
+    assert sq["_p"]._query("stored_chunks") == 0
+    assert np.array_equal(one["gradient"], sq["gradient"])
+    b = run_case(_oracle(prec, "clean"), case)
+    assert close(one["gradient"], b["gradient"], case["jacobians"][0]["n"], prec, TOL_ADJ)
