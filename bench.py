@@ -845,7 +845,10 @@ def main():
                 ("c4_dense_f64", "c4d", {"dtype": "f64"}), ("c4_dense_f64_512steps", "c4d", {"dtype": "f64", "L": 512}),
                 ("c4_replicas_f32", "c4r", {}),
                 # exact schedule (compat=clean): the forward states of all 128 steps stay in HBM (4.6 GB), one sweep, no recompute
-                ("c4_dense_f32_exact_schedule", "c4d", {"dtype": "f32", "compat": "clean"})]
+                ("c4_dense_f32_exact_schedule", "c4d", {"dtype": "f32", "compat": "clean"}),
+                # the headline workload and C4 sparse in the exact schedule: chunk trajectories of the tail chunks stay in free HBM
+                ("c3_exact_schedule", "c3", {"compat": "clean"}),
+                ("c4_sparse_f32_exact_schedule", "c4s", {"dtype": "f32", "compat": "clean"})]
         for key, wk, over in plan:
             ww = dict(WORKLOADS[wk], **{k: v for k, v in over.items() if k != "compat"})
             aa = argparse.Namespace(**dict(vars(a), compat=over["compat"])) if "compat" in over else a
