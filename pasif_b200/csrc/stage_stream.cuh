@@ -39,8 +39,27 @@ struct StreamArgs {
   // drawn their last tile; the last of them resets both for the next launch on the same stream.  A CTA that starts late
   // (its SM was busy with the GEMM of another part) then takes what is left instead of a fixed share of the batch.
   int* sched;
+  // trajectory -> instance without a division: q = (n * e_mul) >> e_sh equals n / E for every n < 2^31 (e_mul = ceil(2^e_sh / E),
+  // e_sh = 31 + ceil(log2 E); checked on the host); e_mul == 0: plain division
+  unsigned e_mul;
+  int e_sh;
 };
 constexpr int STREAM_MAXBUF = 4;
+
+// wait of the 34 row warps of an SM for their tile: with a suspend-time hint the warp sleeps in the barrier unit instead of
+// re-issuing the poll (ncu of the first version: 11 % of the kernel's warp instructions were try_wait / branch pairs)
+__device__ __forceinline__ void mbar_wait_suspend(uint64_t* bar, uint32_t parity) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "SWAIT_LOOP:\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n"
+      "@p bra SWAIT_DONE;\n"
+      "bra SWAIT_LOOP;\n"
+      "SWAIT_DONE:\n"
+      "}\n" ::"r"(pasif_tc::smem_u32(bar)), "r"(parity), "r"(20000u)
+      : "memory");
+}
 
 __device__ __forceinline__ void bulk_load(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
   asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(pasif_tc::smem_u32(dst)), "l"(src),
@@ -141,15 +160,21 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
   uint32_t phase = 0;
   for (;;) {
     // the producer names the tile of a buffer before it arrives on (or hands the loads to) the buffer's barrier
-    pasif_tc::mbar_wait(&full[buf], phase);
+    mbar_wait_suspend(&full[buf], phase);
     const int tile = tile_of[buf];
     if (tile < 0) break;
     const long long p0 = (long long)tile * TT;
     const int nb = (int)min((long long)TT, (long long)u.n_traj - p0);
     const unsigned pg0 = (unsigned)(u.p_base + p0);
-    const unsigned inst0 = pg0 / E, e0 = pg0 - inst0 * E;
+    const unsigned inst0 = a.e_mul ? (unsigned)(((unsigned long long)pg0 * a.e_mul) >> a.e_sh) : pg0 / E;
+    const unsigned e0 = pg0 - inst0 * E;
     unsigned ib[TT], eb[TT];
-    {
+    if constexpr (UNI) {
+      // one instance per tile (TT divides E and the part's offset): consecutive excitations of instance inst0; slots past the
+      // batch cannot occur (the batch is a multiple of E, hence of TT)
+#pragma unroll
+      for (int b = 0; b < TT; ++b) { ib[b] = inst0; eb[b] = e0 + (unsigned)b; }
+    } else {
       unsigned i = inst0, e = e0;
 #pragma unroll
       for (int b = 0; b < TT; ++b) {
@@ -231,8 +256,17 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
     }
     // ---- force
     if (u.fe) {
+      if constexpr (UNI && TT == 4 && sizeof(T) == 4) {
+        // the tile's four excitation samples are consecutive and 16-byte aligned (e0 and E are multiples of 4): one request
+        const float4 f = __ldg(reinterpret_cast<const float4*>(u.fe + e0));
+        y[0] = fma(cf, (T)f.x, y[0]); y[1] = fma(cf, (T)f.y, y[1]); y[2] = fma(cf, (T)f.z, y[2]); y[3] = fma(cf, (T)f.w, y[3]);
+      } else if constexpr (UNI && TT == 2 && sizeof(T) == 8) {
+        const double2 f = __ldg(reinterpret_cast<const double2*>(u.fe + e0));
+        y[0] = fma(cf, (T)f.x, y[0]); y[1] = fma(cf, (T)f.y, y[1]);
+      } else {
 #pragma unroll
-      for (int b = 0; b < TT; ++b) y[b] = fma(UNI ? cf : coef(b, off_f), __ldg(u.fe + eb[b]), y[b]);
+        for (int b = 0; b < TT; ++b) y[b] = fma(UNI ? cf : coef(b, off_f), __ldg(u.fe + eb[b]), y[b]);
+      }
     }
     // the tile is in registers: hand the buffer back before the stores go out
     __syncwarp();
@@ -245,7 +279,7 @@ __global__ void __launch_bounds__(BLK, MINB) stage_update_stream_kernel(const St
     T* __restrict__ Vg = u.Qsave ? u.Qsave + (size_t)p0 * NR + r : nullptr;
 #pragma unroll
     for (int b = 0; b < TT; ++b) {
-      if (b < nb) {
+      if (UNI || b < nb) {                                               // (UNI: every tile is full)
         T xn;
         if constexpr (STAGE == 1) { Sg[b * NR] = y[b]; xn = fma(u.h2, y[b], q[b]); }
         else if constexpr (STAGE == 2) { Sg[b * NR] = fma(T(2), y[b], sv[b]); xn = fma(u.h2, y[b], q[b]); }
