@@ -44,6 +44,52 @@ float run(const float* kh, const float* kl, const float* x, float* y, int NR, in
   return ms * 1000.f / reps;
 }
 
+// fixed cost of a launch of this shape: nothing / barriers + TMEM allocation / + one TMA round trip
+__global__ void __launch_bounds__(192, 1) k_empty(int* out) { if (out && threadIdx.x == 999) *out = 1; }
+__global__ void __launch_bounds__(192, 1) k_prologue(const __grid_constant__ CUtensorMap mapA, int tma, int cols) {
+  using namespace pasif_tc;
+  extern __shared__ unsigned char raw[];
+  unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = reinterpret_cast<uint64_t*>(base + 65536);
+  uint32_t* slot = reinterpret_cast<uint32_t*>(full + 4);
+  const int warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < 4; ++s) mbar_init(&full[s], 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+  }
+  if (warp == 2 && cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(slot)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  if (tma) {
+    if (threadIdx.x == 128) {
+      mbar_expect_tx(&full[0], 8192);
+      tma_load_2d(base, &mapA, &full[0], 0, blockIdx.y * 128);
+    }
+    mbar_wait(&full[0], 0);
+  }
+  __syncthreads();
+  if (warp == 2 && cols) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(*slot), "r"(cols) : "memory");
+}
+template <typename F>
+float time_launches(F launch, int reps) {
+  cudaEvent_t a, b;
+  CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
+  for (int i = 0; i < 3; ++i) launch();
+  CK(cudaDeviceSynchronize());
+  CK(cudaEventRecord(a));
+  for (int i = 0; i < reps; ++i) launch();
+  CK(cudaEventRecord(b));
+  CK(cudaDeviceSynchronize());
+  float ms;
+  CK(cudaEventElapsedTime(&ms, a, b));
+  return ms * 1000.f / reps;
+}
+
 template <int NT>
 float run_pair(const float* kh, const float* kl, const float* x, float* y, int NR, int P, int m_lo, int m_hi, int reps) {
   typedef pasif_tc::Tc2Cfg<NT> Cfg;
@@ -100,6 +146,17 @@ int main(int argc, char** argv) {
   R(256, 32, 0, 0, 256, 512, "256-row tile, bk32, 2 stages");
   R(256, 16, 0, 0, 0, 512, "adjoint band: 512 rows, bk16 (2 row tiles per trajectory tile)");
   R(256, 16, 16, 0, 0, 512, "  direct stores from registers (first version)");
+  {
+    CUtensorMap mA = make_map(x, P, NR, 128, 16);
+    CK(cudaFuncSetAttribute(k_empty, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    CK(cudaFuncSetAttribute(k_prologue, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    dim3 grid(1, P / 128);
+    printf("%-64s %7.2f us\n", "empty kernel, same grid / block, no dynamic shared memory", time_launches([&] { k_empty<<<grid, 192>>>(nullptr); }, reps));
+    printf("%-64s %7.2f us\n", "empty kernel, 198 KB dynamic shared memory", time_launches([&] { k_empty<<<grid, 192, 198 * 1024>>>(nullptr); }, reps));
+    printf("%-64s %7.2f us\n", "  + barriers, tensor-map prefetch, __syncthreads", time_launches([&] { k_prologue<<<grid, 192, 198 * 1024>>>(mA, 0, 0); }, reps));
+    printf("%-64s %7.2f us\n", "  + TMEM alloc / dealloc of 256 columns", time_launches([&] { k_prologue<<<grid, 192, 198 * 1024>>>(mA, 0, 256); }, reps));
+    printf("%-64s %7.2f us\n", "  + one TMA load of the X tile and the wait for it", time_launches([&] { k_prologue<<<grid, 192, 198 * 1024>>>(mA, 1, 256); }, reps));
+  }
   printf("%-64s %7.2f us\n", "CTA pairs (cta_group::2), forward band, one 256-row tile", run_pair<1>(kh, kl, x, y, NR, P, 256, 512, reps));
   printf("%-64s %7.2f us\n", "CTA pairs, adjoint band, two 256-row tiles per pair", run_pair<2>(kh, kl, x, y, NR, P, 0, 512, reps));
   printf("%-64s %7.2f us\n", "CTA pairs, adjoint band, one tile per pair (2 waves)", run_pair<1>(kh, kl, x, y, NR, P, 0, 512, reps));
