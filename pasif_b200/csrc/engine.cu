@@ -524,6 +524,7 @@ struct pasif_engine {
   bool stream_dynamic = false;                   // ... tiles drawn from a counter instead of a fixed share per CTA
   long long stage_enqueue_us = 0;                // host time the last dense-operator gradient spent queueing launches
   DevBuf stage_sched;                            // ... the counters: (next tile, finished CTAs) per part
+  int dg_bm = 32;                                // fp64 stage GEMM (DMMA): rows per CTA tile (32: four CTAs of 4 warps per SM; 64: two of 8)
   int tc_stages = 0;                             // fused-split GEMM: pipeline stages (0: as many as fit an SM)
   bool stage_dephase = false;                    // parts start one GEMM apart, so GEMMs run beside the neighbour's updates
   std::vector<cudaStream_t> part_streams;
@@ -1632,6 +1633,10 @@ int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
     e->stream_grid_ctas = t;
   } else if (k == "stream_dynamic") {
     e->stream_dynamic = (v == "on" || v == "1");
+  } else if (k == "dg_bm") {
+    const int t = std::atoi(v.c_str());
+    if (t != 32 && t != 64) throw std::runtime_error("dg_bm must be 32 or 64");
+    e->dg_bm = t;
   } else if (k == "tc_stages") {
     const int t = std::atoi(v.c_str());
     if (t != 0 && (t < 2 || t > 6)) throw std::runtime_error("tc_stages must be 0 (auto) or 2..6");

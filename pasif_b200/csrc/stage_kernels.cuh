@@ -274,8 +274,17 @@ __global__ void stage_scatter_kernel(const T* __restrict__ Q, const int* __restr
 // Mpad % 64 == 0, Ppad % 128 == 0, K % 16 == 0.  CTA tile 64 (m) x 128 (p), 8 warps as 2 x 4, warp tile 32 x 32,
 // 3-stage cp.async pipeline; shared-memory rows padded to 20 doubles so that every DMMA fragment load (8 rows x 4
 // consecutive doubles per half-warp) is bank-conflict free.
+// The tile height BM is a template parameter: 64 rows (8 warps as 2 x 4, three stages, two CTAs per SM) or 32 rows (4 warps,
+// two stages, four CTAs per SM).  The C4 bands give 512 (forward) / 1024 (adjoint) tiles of 64 rows for 148 SMs -- 3.46 / 6.92
+// tiles per SM, so the busiest SMs run 4 / 7 and the launch ends at 0.865 / 0.99 of a balanced one; with 32-row tiles the
+// imbalance is at most one half-size tile.
 constexpr int DG_BM = 64, DG_BN = 128, DG_BK = 16, DG_LD = 20, DG_STAGES = 3;
 constexpr int DG_SMEM = DG_STAGES * (DG_BM + DG_BN) * DG_LD * 8;
+template <int BM, int STAGES>
+struct DgCfg {
+  static constexpr int THREADS = BM * 4;                              // (BM / 32) x 4 warps
+  static constexpr int SMEM = STAGES * (BM + DG_BN) * DG_LD * 8;
+};
 
 __device__ __forceinline__ void cp_async16(void* smem, const void* gmem) {
   const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
@@ -286,8 +295,10 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N)); }
 
 // lda / ldb: row strides of A / B (both pointers already offset to the first column of the K band)
-__global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B,
-                                                            double* __restrict__ Y, int M, int K, int ldy, int lda, int ldb) {
+template <int DG_BM = 64, int DG_STAGES = 3>
+__global__ void __launch_bounds__(DG_BM * 4) dgemm_tn_dmma_kernel(const double* __restrict__ A, const double* __restrict__ B,
+                                                                  double* __restrict__ Y, int M, int K, int ldy, int lda, int ldb) {
+  constexpr int NTHR = DG_BM * 4;
   extern __shared__ __align__(16) unsigned char dg_smem[];
   double* sA = reinterpret_cast<double*>(dg_smem);                    // [STAGES][BM][LD]
   double* sB = sA + DG_STAGES * DG_BM * DG_LD;                        // [STAGES][BN][LD]
@@ -305,12 +316,12 @@ __global__ void __launch_bounds__(256) dgemm_tn_dmma_kernel(const double* __rest
     double* a = sA + st * DG_BM * DG_LD;
     double* b = sB + st * DG_BN * DG_LD;
 #pragma unroll
-    for (int c = tid; c < DG_BM * 8; c += 256) {
+    for (int c = tid; c < DG_BM * 8; c += NTHR) {
       const int row = c >> 3, ch = c & 7;
       cp_async16(a + row * DG_LD + ch * 2, Ag + (size_t)row * lda + kb * DG_BK + ch * 2);
     }
 #pragma unroll
-    for (int c = tid; c < DG_BN * 8; c += 256) {
+    for (int c = tid; c < DG_BN * 8; c += NTHR) {
       const int row = c >> 3, ch = c & 7;
       cp_async16(b + row * DG_LD + ch * 2, Bg + (size_t)row * ldb + kb * DG_BK + ch * 2);
     }

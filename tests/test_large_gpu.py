@@ -326,3 +326,15 @@ def test_dense_operator_exact_schedule_in_one_chunk(prec):
     assert np.array_equal(one["gradient"], sq["gradient"])
     b = run_case(_oracle(prec, "clean"), case)
     assert close(one["gradient"], b["gradient"], case["jacobians"][0]["n"], prec, TOL_ADJ)
+
+
+def test_fp64_gemm_tile_heights_are_bit_identical():
+    """fp64 stage GEMM (DMMA): 32-row tiles (default: four CTAs of four warps per SM, so the SMs finish within one small tile of
+    each other) and 64-row tiles accumulate every element over k in the same order -- gradients equal bit for bit."""
+    case = chain_case(256, True, E=130, L=6)
+    case["traj_save_steps"] = None
+    a = run_case(capi.engine_class("f64"), case, options={"dg_bm": "64"})
+    b = run_case(capi.engine_class("f64"), case)
+    assert a["_p"]._query("large_stage_classes") >= 1
+    for key in ("amplitudes", "gradient"):
+        assert np.array_equal(a[key], b[key]), key
