@@ -310,6 +310,9 @@ __global__ void __launch_bounds__(DG_BM * 4) dgemm_tn_dmma_kernel(const double* 
   const double* Ag = A + (size_t)m0 * lda;
   const double* Bg = B + (size_t)p0 * ldb;
   const int nkb = K / DG_BK;
+  // programmatic dependent launch (no-ops for a normal launch): the successor may be scheduled, the predecessor has completed
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  asm volatile("griddepcontrol.wait;" ::: "memory");
 
   auto issue = [&](int kb, int st) {
     // A tile: 64 rows x 16 doubles = 512 16-byte chunks; B tile: 128 rows -> 1024 chunks
