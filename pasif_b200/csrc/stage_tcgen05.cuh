@@ -219,7 +219,6 @@ __device__ __forceinline__ float tf32_rna(float x) {
   return __uint_as_float(u);
 }
 
-// PROBE (tools/probe_gemm_parts.cu only; 0 in the library): 1 no hi/lo arithmetic, 2 no MMAs, 4 no TMA loads, 8 no stores
 // Epilogue of the fused-split kernels.  A thread holds 32 consecutive columns of ONE trajectory after tcgen05.ld; stored
 // directly, a warp instruction would touch 32 different lines (measured: 6 of the kernel's 27 us, tools/probe_gemm_parts.cu).
 // Instead every 32 x 32 block goes through shared memory (the pipeline stages are free once `done` has fired; ebuf: 2 x 4 KB
@@ -230,11 +229,8 @@ template <int NCHUNK, int PROBE>
 __device__ __forceinline__ void epilogue_bulk_store(uint32_t tmem_d, int warp, int lane, unsigned char* ebuf, const CUtensorMap* mapY, float* Y, int ldy,
                                                     int m0, int M, int p0) {
   float* yrow = Y + (size_t)(p0 + warp * 32 + lane) * ldy;
-#pragma unroll 1
-  for (int c = 0; c < NCHUNK; ++c) {
-    const int mc = m0 + c * 32;
-    if (mc >= M) break;
-    uint32_t v[32];
+  // tcgen05.ld of chunk c + 1 is in flight while chunk c goes through shared memory (two register sets, loop unrolled by two)
+  auto tmem_ld = [&](uint32_t (&v)[32], int c) {
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32);
     asm volatile(
         "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, "
@@ -244,7 +240,10 @@ __device__ __forceinline__ void epilogue_bulk_store(uint32_t tmem_d, int warp, i
           "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]),
           "=r"(v[31])
         : "r"(taddr));
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+  };
+  auto put = [&](const uint32_t (&v)[32], int c) {
+    const int mc = m0 + c * 32;
+    if (mc >= M) return;                                    // (M, the end of the band, and the tile origin are multiples of 32)
     if constexpr ((PROBE & 16) != 0) {                      // (probe: the direct stores of the first version)
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
@@ -269,11 +268,25 @@ __device__ __forceinline__ void epilogue_bulk_store(uint32_t tmem_d, int warp, i
         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
       }
     }
+  };
+  uint32_t va[32], vb[32];
+  tmem_ld(va, 0);
+#pragma unroll 1
+  for (int c = 0; c < NCHUNK; c += 2) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    if (c + 1 < NCHUNK) tmem_ld(vb, c + 1);
+    put(va, c);
+    if (c + 1 < NCHUNK) {
+      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      if (c + 2 < NCHUNK) tmem_ld(va, c + 2);
+      put(vb, c + 1);
+    }
   }
   // shared memory must outlive the reads of the bulk stores; their global writes complete with the grid
   if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
+// PROBE (tools/probe_gemm_parts.cu only; 0 in the library): 1 no hi/lo arithmetic, 2 no MMAs, 4 no TMA loads, 8 no stores
 template <int TC_BN, int BK = TC_BK, int PROBE = 0>
 __global__ void __launch_bounds__(192, 1) sgemm_tn_3xtf32_tcgen05_split_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                                const __grid_constant__ CUtensorMap mapBh,
