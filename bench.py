@@ -677,6 +677,8 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
     })
     if stage and enqueue_ms > 0:
         entry["host_enqueue_ms_per_step"] = enqueue_ms
+        if _has_query(p, "stage_graph_replays"):
+            entry["cuda_graph_replays"] = int(p._query("stage_graph_replays"))
     if do_e2e:
         entry["e2e"] = {"value": tot_pairs * e2e_steps / e2e_t, "unit": "gradient evals/s", "h2d_bytes_per_step": int(p._query("last_h2d_bytes")),
                         "d2h_bytes_per_step": int(d2h_bytes), "steps": e2e_steps,

@@ -522,6 +522,15 @@ struct pasif_engine {
   int stream_grid = 0;                           // ... CTAs per SM in the grid (0: stream_ctas)
   int stream_grid_ctas = 0;                      // ... or the absolute number of CTAs (0: per SM as above)
   bool stream_dynamic = false;                   // ... tiles drawn from a counter instead of a fixed share per CTA
+  // dense-operator path: the launch sequence of a gradient as an instantiated CUDA graph (stage_host.inc)
+  struct StageGraphT {
+    cudaGraphExec_t exec = nullptr;
+    std::vector<uint64_t> key, warm_key;
+    long long d_launches = 0, d_gemm = 0, d_kind[5] = {0, 0, 0, 0, 0};
+  } stage_graph;
+  bool stage_graph_on = true;
+  long long stage_graph_replays = 0;
+  uint64_t cfg_gen = 0;                          // bumped by every option / system / excitation change: invalidates the graph
   long long stage_enqueue_us = 0;                // host time the last dense-operator gradient spent queueing launches
   DevBuf stage_sched;                            // ... the counters: (next tile, finished CTAs) per part
   int dg_bm = 32;                                // fp64 stage GEMM (DMMA): rows per CTA tile (32: four CTAs of 4 warps per SM; 64: two of 8)
@@ -805,6 +814,7 @@ bool is_large(const pasif_engine& E, const ClassData& c) {
 
 template <typename T>
 void build_classes(pasif_engine& E, std::vector<ClassData>&& cds, std::vector<DevClass>& out) {
+  ++E.cfg_gen;
   free_classes(out);
   E.d_tail.release();                              // sized for the previous systems
   out.resize(cds.size());
@@ -1107,6 +1117,7 @@ Schedule reference_schedule(uint32_t n) {       // reference src/__GpuDriver.cu:
   return s;
 }
 
+typedef pasif_engine::StageGraphT StageGraph;
 #include "large_host.inc"
 #include "stage_host.inc"
 void LargeClassDeleter::operator()(LargeClass* p) const {
@@ -1360,6 +1371,7 @@ void set_csr(SystemData& s, uint32_t n_rows, uint32_t n_cols, const double* valu
 }
 
 void load_exc(pasif_engine& E, const double* exc, uint32_t n_exc, uint32_t length, uint32_t sample_rate) {
+  if (n_exc != E.E || length != E.L || sample_rate != E.sample_rate) ++E.cfg_gen;   // (same shape: the device buffers stay where they are)
   if (!exc || n_exc == 0 || length == 0) throw std::runtime_error("excitation set must be a non-empty [E][L] array");
   if (sample_rate == 0) throw std::runtime_error("sampleRate must be > 0");
   if (E.have_exc && n_exc != E.E && (E.fwd_ready || E.joint_ready)) {
@@ -1462,6 +1474,7 @@ void pasif_destroy(pasif_engine* e) {
     if (e->stream2) cudaStreamDestroy(e->stream2);
     for (StageBufs*& sb : e->stage_bufs)
       if (sb) { sb->release(); delete sb; sb = nullptr; }
+    if (e->stage_graph.exec) cudaGraphExecDestroy(e->stage_graph.exec);
     for (cudaStream_t st : e->part_streams) cudaStreamDestroy(st);
     for (cudaEvent_t ev : e->part_events) cudaEventDestroy(ev);
     if (e->stream) cudaStreamSynchronize(e->stream);
@@ -1564,7 +1577,10 @@ int pasif_set_modulation(pasif_engine* e, const double* buffer, uint32_t n) {
 int pasif_set_option(pasif_engine* e, const char* key, const char* value) {
   PASIF_TRY(e)
   const std::string k(key ? key : ""), v(value ? value : "");
-  if (k == "compat") {
+  ++e->cfg_gen;
+  if (k == "stage_graph") {
+    e->stage_graph_on = (v == "on" || v == "1");
+  } else if (k == "compat") {
     if (v == "reference") e->compat_clean = false;
     else if (v == "clean") e->compat_clean = true;
     else throw std::runtime_error("compat must be 'reference' or 'clean'");
@@ -1813,6 +1829,7 @@ int pasif_query(const pasif_engine* e, const char* key, double* value) {
   else if (k == "large_stage_classes") *value = (double)e->large_stage_classes;
   else if (k == "gemm_launches") *value = (double)e->gemm_launches;
   else if (k == "stage_enqueue_us") *value = (double)e->stage_enqueue_us;
+  else if (k == "stage_graph_replays") *value = (double)e->stage_graph_replays;
   else if (k == "stage_direct") *value = stage_direct(*e, e->dtype == PASIF_F32 ? 4 : 8) ? 1.0 : 0.0;
   else if (k.rfind("stage_band_", 0) == 0) {
     // rows / columns of K' that go through the per-stage GEMM of the (first) dense-operator class:

@@ -338,3 +338,29 @@ def test_fp64_gemm_tile_heights_are_bit_identical():
     assert a["_p"]._query("large_stage_classes") >= 1
     for key in ("amplitudes", "gradient"):
         assert np.array_equal(a[key], b[key]), key
+
+
+@pytest.mark.parametrize("prec", ["f64", "f32"])
+@pytest.mark.parametrize("compat", ["reference", "clean"])
+def test_dense_operator_gradient_graph_replay(compat, prec):
+    """The launch sequence of a dense-operator gradient is captured into a CUDA graph on the second call with the same
+    configuration and replayed from the third on: every call returns the same bits as the directly queued launches
+    (stage_graph=off), also after new excitations of the same shape have been loaded."""
+    case = chain_case(40, True, E=24, L=60)
+    a = run_case(capi.engine_class(prec, compat), case)
+    p = a["_p"]
+    assert p._query("large_stage_classes") >= 1
+    g = [a["gradient"]] + [np.asarray(p.getGradient()) for _ in range(3)]
+    assert p._query("stage_graph_replays") >= 2
+    for x in g[1:]:
+        assert np.array_equal(x, g[0])
+    off = run_case(capi.engine_class(prec, compat), case, options={"stage_graph": "off"})
+    assert off["_p"]._query("stage_graph_replays") == 0
+    assert np.array_equal(off["gradient"], g[0])
+    # new excitations of the same shape: the graph reads the refreshed device buffer
+    case2 = dict(case, excitations=wl.random_sine_excitations(24, 60, 16000, seed=99))
+    p.setExcitations([np.array(r) for r in case2["excitations"]], case2["sample_rate"])
+    g2 = np.asarray(p.getGradient())
+    ref2 = run_case(capi.engine_class(prec, compat), case2, options={"stage_graph": "off"})
+    assert np.array_equal(g2, ref2["gradient"])
+    assert not np.array_equal(g2, g[0])
