@@ -527,6 +527,7 @@ struct pasif_engine {
     cudaGraphExec_t exec = nullptr;
     std::vector<uint64_t> key, warm_key;
     long long d_launches = 0, d_gemm = 0, d_kind[5] = {0, 0, 0, 0, 0};
+    long long warm_launches = 0;                  // launches of the directly queued call with warm_key
   } stage_graph;
   bool stage_graph_on = true;
   long long stage_graph_replays = 0;
