@@ -605,11 +605,12 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
         if w["dtype"] == "f32":
             tpeak = ctx.peaks.get("bf16_tflops", 1590.0) / 2.0
             tsrc = "tf32 dense = half the bf16 rate: MEASURED_PEAKS.json bf16_tflops / 2" if ctx.peaks else "fallback 1590 / 2"
-            tname = "sgemm_tn_3xtf32_tcgen05_kernel (tcgen05.mma kind::tf32, TMEM accumulator, TMA operands)"
+            tname = ("sgemm_tn_3xtf32_tcgen05_pair_kernel (tcgen05.mma.cta_group::2 kind::tf32, TMEM accumulator, TMA operands and bulk tensor stores; "
+                     "sgemm_tn_3xtf32_tcgen05_split_kernel when the shape does not pair)")
         else:
             tpeak = ctx.fma_peak("dmma")
             tsrc = "register-resident mma.sync.m8n8k4.f64 microbenchmark, same run (tcgen05 has no fp64 kind)"
-            tname = "dgemm_tn_dmma_kernel (mma.sync.m8n8k4.f64, cp.async pipeline)"
+            tname = "dgemm_tn_dmma_kernel<32, 2> (mma.sync.m8n8k4.f64, 32-row tiles, cp.async pipeline)"
         ach = gemm_flops[dom] / (per_kernel[dom]["avg_launch_ms"] * 1e-3) / 1e12
         whole = (flops_gfwd + flops_bwd) / (dev_only_ms * 1e-3) / 1e12
         tensor = {"bound": "tensor", "kernel": tname, "achieved": ach, "peak": tpeak, "unit": "TFLOP/s", "frac": ach / tpeak,
@@ -653,7 +654,7 @@ def measure(ctx, w, a, steps, warmup, *, presharded=True, strong=False, headline
             if u_launch[k]:
                 us = u_ms[k] / u_launch[k] * 1e3
                 gbs = pairs * vals * sz / (us * 1e-6) / 1e9
-                stage_hbm[k] = {"kernel": "stage_update_kernel", "us_per_launch": us, "launches_per_step": u_launch[k] // prof_steps,
+                stage_hbm[k] = {"kernel": "stage_update_stream_kernel", "us_per_launch": us, "launches_per_step": u_launch[k] // prof_steps,
                                 "ms_per_step": u_ms[k] / prof_steps, "algorithmic_bytes_per_launch": pairs * vals * sz,
                                 "achieved_gbs": gbs, "frac_of_hbm_peak": gbs / hbm_peak}
     whole_tf = (flops_gfwd + flops_bwd) / (dev_only_ms * 1e-3) / 1e12
